@@ -1,0 +1,132 @@
+/*
+ * lphash_b200 — C ABI of the B200-native LPHash hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions.
+ * The reference (jermp/lphash) has no FFI of its own; its seam for this path is a C++ member
+ * function, so each entry point below cites the reference interface it replaces
+ * (paths relative to the reference tree; "pthash/" = external/pthash/).  INTEGRATION.md shows
+ * the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns LPHB_OK (0) or a negative LPHB_E_* code; lphb_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - the caller owns all host buffers; the library owns device memory behind opaque handles;
+ *   - one handle = one `.lph` image resident on one GPU; calls on one handle are serialised by
+ *     the caller, different handles (different GPUs) may be driven from different host threads;
+ *   - "batch" = ASCII bases of n_contigs contigs concatenated without separators + offsets
+ *     (n_contigs + 1 entries, offsets[0] need not be 0 but must index `bases`); this is what
+ *     kseq hands the reference one record at a time (src/query.cpp:51-52);
+ *   - there is NO CPU fallback: every call that computes needs a CUDA device and fails with
+ *     LPHB_E_CUDA otherwise.
+ */
+#ifndef LPHASH_B200_H
+#define LPHASH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPHB_OK 0
+#define LPHB_E_ARG (-1)      /* bad argument (null pointer, k/m out of range, ...)            */
+#define LPHB_E_IO (-2)       /* cannot open / read the .lph file                              */
+#define LPHB_E_FORMAT (-3)   /* not a partitioned-LP-MPHF image (truncated, trailing bytes...) */
+#define LPHB_E_CUDA (-4)     /* CUDA error or no device                                       */
+#define LPHB_E_CAPACITY (-5) /* output buffer too small; required size reported where possible */
+#define LPHB_E_NOMEM (-6)
+
+typedef struct lphb_mphf lphb_mphf; /* device image of one lphash::mphf on one GPU */
+
+/* Header fields of the serialized lphash::mphf (include/partitioned_mphf.hpp:204-211, :42-48). */
+typedef struct lphb_info {
+    uint32_t k, m;
+    uint32_t kmer_bits; /* 64 or 128: the kmer_t the file was built with (compile_constants.tpd) */
+    int32_t device;
+    uint64_t mm_seed;
+    uint64_t nkmers;
+    uint64_t distinct_minimizers;
+    uint64_t n_maximal;
+    uint64_t right_coll_sizes_start;
+    uint64_t none_sizes_start;
+    uint64_t none_pos_start;
+    uint64_t fallback_keys; /* k-mers handled by fallback_kmer_order */
+    uint64_t file_bytes;    /* size of the .lph image parsed                                    */
+    uint64_t device_bytes;  /* bytes of HBM the device image occupies                           */
+} lphb_info;
+
+const char* lphb_last_error(void);
+const char* lphb_version(void);
+int lphb_device_count(int* count);
+
+/* ---- loading: replaces essentials::load(hf, file) (src/query.cpp:37) ----------------------
+ * Parses the byte-exact essentials visitor image of lphash::mphf
+ * (include/partitioned_mphf.hpp:204-219) and uploads a flat device image.  kmer_bits selects the
+ * fallback hash flavour of include/constants.hpp:56-70 (the file does not record it).          */
+int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out);
+int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device,
+                          lphb_mphf** out);
+int lphb_mphf_free(lphb_mphf* f);
+int lphb_mphf_info(const lphb_mphf* f, lphb_info* info);
+
+/* ---- query-p hot call ----------------------------------------------------------------------
+ * Replaces `hf(seq->seq.s, seq->seq.l, true)` = lphash::mphf::operator()(contig, len,
+ * streaming=true) (include/partitioned_mphf.hpp:73-184; caller src/query.cpp:52) for a whole
+ * batch of contigs.  HOST buffers in, HOST buffers out (H2D / D2H copies happen inside).
+ *   codes         receives the hash codes of all contigs, concatenated in contig order
+ *   code_offsets  (n_contigs + 1) receives where each contig's codes start; contig c produced
+ *                 code_offsets[c+1] - code_offsets[c] codes: L-k+1 for an ACGT-only contig of
+ *                 length L >= k, 0 if L < k; contigs with other bytes follow the reference's
+ *                 streaming behaviour exactly (its spurious entries included)
+ *   n_codes       total number of codes (also set when returning LPHB_E_CAPACITY)              */
+int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets,
+                      uint64_t n_contigs, uint64_t* codes, uint64_t codes_capacity,
+                      uint64_t* code_offsets, uint64_t* n_codes);
+
+/* Device-resident variant: d_* are device pointers on the handle's GPU, `stream` is a
+ * cudaStream_t (NULL = default stream).  Asynchronous.  h_offsets is the host copy of the same
+ * offsets (used only for sizes).  Evaluates the stateless definition (one code per window of k
+ * valid bases); d_status[0] = number of codes laid out (sum of max(0, L-k+1)), d_status[1] =
+ * number of contigs containing a non-ACGT byte (their code ranges then hold only the valid
+ * k-mers' codes; lphb_query_stream runs the exact fix-up for those, this call does not).       */
+int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* d_offsets,
+                             const uint64_t* h_offsets, uint64_t n_contigs, uint64_t* d_codes,
+                             uint64_t codes_capacity, uint64_t* d_code_offsets,
+                             uint64_t* d_status, void* stream);
+
+/* ---- build-p Part 1: minimizer / super-k-mer scan -------------------------------------------
+ * Replaces the loop over minimizer::from_string (include/minimizer.hpp:11-170; caller
+ * src/partitioned_mphf.cpp:70-77) for a batch of contigs.  records receives packed 18-byte
+ * mm_record_t {u64 itself, u64 id, u8 p1, u8 size} (include/constants.hpp:26-33) in scan order;
+ * mm_count is the running global m-mer ordinal (in: value before the batch, out: after).        */
+int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                         const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
+                         void* records, uint64_t records_capacity, uint64_t* n_records,
+                         uint64_t* n_kmers);
+
+/* ---- build-p Part 4: k-mers of colliding minimizers -----------------------------------------
+ * Replaces the loop over minimizer::get_colliding_kmers (include/minimizer.hpp:172-319; caller
+ * src/partitioned_mphf.cpp:120-129).  ids = ascending minimizer-occurrence ids (classify's second
+ * output).  kmers receives kmer_bits/8 little-endian bytes per k-mer, in scan order.            */
+int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                         const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
+                         const uint64_t* ids, uint64_t n_ids, int kmer_bits, void* kmers,
+                         uint64_t kmers_capacity, uint64_t* n_kmers);
+
+/* ---- pinned host memory (optional; makes the copies inside lphb_query_stream asynchronous) -- */
+int lphb_host_alloc(void** ptr, uint64_t nbytes);
+int lphb_host_free(void* ptr);
+
+/* Counters for the last lphb_query_stream* call on the handle (kernel launches, device ms). */
+typedef struct lphb_stats {
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t dirty_contigs;
+    double kernel_ms; /* CUDA-event time of the main kernel(s), host-buffer calls only */
+} lphb_stats;
+int lphb_mphf_stats(const lphb_mphf* f, lphb_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPHASH_B200_H */

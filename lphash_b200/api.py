@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's `lphash::mphf` query interface on top of the C ABI
+(include/lphash_b200.h, built into lphash_b200/liblphash_b200.so).
+
+Reference interface mirrored (/root/reference/include/partitioned_mphf.hpp:13-39):
+    hf = mphf(); essentials::load(hf, file)        ->  hf = Mphf.load(file, kmer_bits)
+    hf(contig, len, streaming=true)                 ->  hf(contig)            (np.uint64 array)
+    hf.get_kmer_count(), hf.get_minimizer_L0()      ->  same names
+Batch entry points (`query_batch`, `query_device`) are what a driver that wants throughput calls:
+one C-ABI call for many contigs.
+
+There is no CPU implementation behind this module: if the CUDA library is missing or no GPU is
+visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblphash_b200.so")
+
+RECORD_DTYPE = np.dtype([("itself", "<u8"), ("id", "<u8"), ("p1", "u1"), ("size", "u1")])  # mm_record_t
+
+OK, E_ARG, E_IO, E_FORMAT, E_CUDA, E_CAPACITY, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+
+
+class LphashError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lphash_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Info(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_uint32), ("kmer_bits", C.c_uint32), ("device", C.c_int32),
+                ("mm_seed", C.c_uint64), ("nkmers", C.c_uint64), ("distinct_minimizers", C.c_uint64),
+                ("n_maximal", C.c_uint64), ("right_coll_sizes_start", C.c_uint64),
+                ("none_sizes_start", C.c_uint64), ("none_pos_start", C.c_uint64),
+                ("fallback_keys", C.c_uint64), ("file_bytes", C.c_uint64), ("device_bytes", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("dirty_contigs", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+# every symbol include/lphash_b200.h declares (tests check the library exports all of them)
+EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_load_file",
+           "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
+           "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
+           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats"]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA extension.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                          " (or make -C lphash_b200/csrc)")
+    L = C.CDLL(LIB_PATH)
+    u64, p, i32 = C.c_uint64, C.c_void_p, C.c_int
+    L.lphb_last_error.restype = C.c_char_p
+    L.lphb_version.restype = C.c_char_p
+    L.lphb_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.lphb_mphf_load_file.argtypes = [C.c_char_p, i32, i32, C.POINTER(p)]
+    L.lphb_mphf_load_memory.argtypes = [p, u64, i32, i32, C.POINTER(p)]
+    L.lphb_mphf_free.argtypes = [p]
+    L.lphb_mphf_info.argtypes = [p, C.POINTER(Info)]
+    L.lphb_mphf_stats.argtypes = [p, C.POINTER(Stats)]
+    L.lphb_query_stream.argtypes = [p, p, p, u64, p, u64, p, C.POINTER(u64)]
+    L.lphb_query_stream_device.argtypes = [p, p, p, p, u64, p, u64, p, p, p]
+    L.lphb_scan_superkmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
+                                       u64, C.POINTER(u64), C.POINTER(u64)]
+    L.lphb_colliding_kmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
+                                       u64, i32, p, u64, C.POINTER(u64)]
+    L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
+    L.lphb_host_free.argtypes = [p]
+    for name in EXPORTS:
+        if getattr(L, name).restype is C.c_int:
+            pass
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise LphashError(rc, lib().lphb_last_error().decode())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().lphb_device_count(C.byref(n)))
+    return n.value
+
+
+def _as_batch(bases, offsets):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    if offsets.ndim != 1 or len(offsets) < 1:
+        raise ValueError("offsets must have n_contigs + 1 entries")
+    return bases, offsets
+
+
+class Mphf:
+    """A partitioned LP-MPHF resident on one GPU (the reference's `lphash::mphf`, query side)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        info = Info()
+        _check(lib().lphb_mphf_info(self._h, C.byref(info)))
+        self.info = info
+        self.k, self.m, self.kmer_bits, self.device = info.k, info.m, info.kmer_bits, info.device
+
+    # -- construction ------------------------------------------------------------------------
+    @classmethod
+    def load(cls, path: str, kmer_bits: int = 64, device: int = 0) -> "Mphf":
+        """essentials::load(hf, path) (/root/reference/src/query.cpp:37)."""
+        h = C.c_void_p()
+        _check(lib().lphb_mphf_load_file(os.fsencode(path), kmer_bits, device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_bytes(cls, image: bytes, kmer_bits: int = 64, device: int = 0) -> "Mphf":
+        h = C.c_void_p()
+        buf = (C.c_char * len(image)).from_buffer_copy(image)
+        _check(lib().lphb_mphf_load_memory(C.addressof(buf), len(image), kmer_bits, device, C.byref(h)))
+        return cls(h.value)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().lphb_mphf_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference-named accessors -----------------------------------------------------------
+    def get_kmer_count(self) -> int:
+        return self.info.nkmers
+
+    def get_minimizer_L0(self) -> int:
+        return self.info.distinct_minimizers
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(lib().lphb_mphf_stats(self._h, C.byref(s)))
+        return s
+
+    # -- queries -----------------------------------------------------------------------------
+    def __call__(self, contig, streaming: bool = True) -> np.ndarray:
+        """hf(contig, len, streaming): hash codes of the contig's k-mers.  The two modes of the
+        reference agree on ACGT-only input; `streaming=False` is served by the
+        same device path (its reference branch maps non-ACGT to 'A', which is not reproduced)."""
+        if isinstance(contig, str):
+            contig = contig.encode()
+        bases = np.frombuffer(bytes(contig), dtype=np.uint8)
+        offsets = np.array([0, len(bases)], dtype=np.uint64)
+        codes, _ = self.query_batch(bases, offsets)
+        return codes
+
+    def query_batch(self, bases, offsets, out: np.ndarray | None = None):
+        """One C-ABI call for a batch: returns (codes, code_offsets) with HOST arrays in and out."""
+        bases, offsets = _as_batch(bases, offsets)
+        n = len(offsets) - 1
+        lens = np.diff(offsets).astype(np.int64)
+        if (lens < 0).any():
+            raise ValueError("offsets must be non-decreasing")
+        if len(offsets) and int(offsets[-1]) > len(bases):
+            raise ValueError("offsets index past the end of bases")
+        # capacity: clean contigs give L-k+1; contigs with non-ACGT bytes can give up to L-m+1
+        cap = int(np.maximum(lens - self.m + 1, 0).sum()) if out is None else len(out)
+        codes = np.empty(max(cap, 1), dtype=np.uint64) if out is None else out
+        code_off = np.empty(n + 1, dtype=np.uint64)
+        total = C.c_uint64(0)
+        _check(lib().lphb_query_stream(self._h, bases.ctypes.data, offsets.ctypes.data, n,
+                                       codes.ctypes.data, cap, code_off.ctypes.data, C.byref(total)))
+        return codes[: total.value], code_off
+
+    def query_device(self, d_bases: int, d_offsets: int, h_offsets: np.ndarray, d_codes: int,
+                     capacity: int, d_code_offsets: int, d_status: int, stream: int = 0) -> None:
+        """Device-resident asynchronous variant; arguments are raw device pointers (ints), e.g.
+        torch_tensor.data_ptr(), and a cudaStream_t handle."""
+        h_offsets = np.ascontiguousarray(h_offsets, dtype=np.uint64)
+        _check(lib().lphb_query_stream_device(self._h, d_bases, d_offsets, h_offsets.ctypes.data,
+                                              len(h_offsets) - 1, d_codes, capacity, d_code_offsets,
+                                              d_status, stream))
+
+
+# ---- build-side scan (module-level like the reference's free functions in namespace minimizer) --
+
+def scan_superkmers(bases, offsets, k: int, m: int, seed: int = 42, mm_count: int = 0, device: int = 0):
+    """minimizer::from_string over a batch (/root/reference/include/minimizer.hpp:11-170).
+    Returns (records[RECORD_DTYPE] in scan order, n_kmers, mm_count_out)."""
+    bases, offsets = _as_batch(bases, offsets)
+    n = len(offsets) - 1
+    lens = np.diff(offsets).astype(np.int64)
+    cap = int(np.maximum(lens - k + 1, 0).sum()) + n + 1
+    rec = np.empty(max(cap, 1), dtype=RECORD_DTYPE)
+    mm = C.c_uint64(mm_count)
+    nrec, nk = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().lphb_scan_superkmers(device, k, m, seed, bases.ctypes.data, offsets.ctypes.data, n,
+                                      C.byref(mm), rec.ctypes.data, cap, C.byref(nrec), C.byref(nk)))
+    return rec[: nrec.value], nk.value, mm.value
+
+
+def colliding_kmers(bases, offsets, k: int, m: int, ids, seed: int = 42, kmer_bits: int = 64,
+                    mm_count: int = 0, device: int = 0) -> np.ndarray:
+    """minimizer::get_colliding_kmers over a batch (/root/reference/include/minimizer.hpp:172-319).
+    Returns an (n, kmer_bits // 64) uint64 array, column 0 = low word."""
+    bases, offsets = _as_batch(bases, offsets)
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    n = len(offsets) - 1
+    words = kmer_bits // 64
+    cap = int(np.maximum(np.diff(offsets).astype(np.int64) - k + 1, 0).sum())
+    out = np.empty((max(cap, 1), words), dtype=np.uint64)
+    mm = C.c_uint64(mm_count)
+    nk = C.c_uint64(0)
+    _check(lib().lphb_colliding_kmers(device, k, m, seed, bases.ctypes.data, offsets.ctypes.data, n,
+                                      C.byref(mm), ids.ctypes.data, len(ids), kmer_bits,
+                                      out.ctypes.data, cap, C.byref(nk)))
+    return out[: nk.value]

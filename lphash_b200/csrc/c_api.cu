@@ -1,0 +1,623 @@
+// C ABI of lphash_b200 (include/lphash_b200.h): handle management, host<->device staging and
+// kernel sequencing.  No CPU implementation of the path exists here: without a CUDA device every
+// computing entry point fails with LPHB_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lphash_b200.h"
+#include "lph_image.h"
+#include "query_kernels.cuh"
+#include "scan_kernels.cuh"
+
+using namespace lphb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, std::string const& msg) {
+    g_err = msg;
+    return code;
+}
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+};
+#define CK(expr)                                              \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) throw CudaError{e__, #expr}; \
+    } while (0)
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void* p = nullptr;
+    uint64_t cap = 0;
+    void reserve(uint64_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        uint64_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct Workspace {
+    DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2;
+    unsigned long long* h_status = nullptr;  // pinned, 4 words
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void init() {
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&h_status), 4 * sizeof(unsigned long long)));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        status.reserve(4 * sizeof(unsigned long long));
+    }
+    void destroy() {
+        for (DevBuf* b : {&bases, &offsets, &code_off, &codes, &dirty, &status, &tmp, &aux0, &aux1,
+                          &aux2, &aux3, &codes2})
+            b->release();
+        if (h_status) cudaFreeHost(h_status);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+bool is_host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+struct lphb_mphf {
+    int device = 0;
+    DevImage img{};
+    void* d_arena = nullptr;
+    lphb_info info{};
+    lphb_stats stats{};
+    bool events_pending = false;
+    Workspace ws;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        CK(cudaGetDevice(&prev));
+        if (prev != dev) CK(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class F>
+int guarded(F&& body) {
+    try {
+        return body();
+    } catch (CudaError const& e) {
+        cudaGetLastError();
+        return fail(LPHB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e.e) + " in " + e.what);
+    } catch (FormatError const& e) {
+        return fail(LPHB_E_FORMAT, e.what());
+    } catch (std::bad_alloc const&) {
+        return fail(LPHB_E_NOMEM, "out of host memory");
+    } catch (std::exception const& e) {
+        return fail(LPHB_E_ARG, e.what());
+    }
+}
+
+int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_mphf** out) {
+    if (!out) return fail(LPHB_E_ARG, "out is null");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        ImageBuilder builder;
+        builder.parse(data, n, kmer_bits);  // host-only: format errors surface before any CUDA call
+        int count = 0;
+        CK(cudaGetDeviceCount(&count));
+        if (device < 0 || device >= count) return fail(LPHB_E_CUDA, "no such CUDA device");
+        DeviceGuard g(device);
+        auto* f = new lphb_mphf();
+        try {
+            f->device = device;
+            auto const& arena = builder.arena();
+            CK(cudaMalloc(&f->d_arena, arena.size() + 256));
+            CK(cudaMemcpy(f->d_arena, arena.data(), arena.size(), cudaMemcpyHostToDevice));
+            f->img = builder.rebased(f->d_arena);
+            f->ws.init();
+            // collision_base = EF[none_pos_start] + w*n_maximal, evaluated once by the device's
+            // own EF code (src/partitioned_mphf.cpp:308-311)
+            launch_collision_base(f->img, reinterpret_cast<uint64_t*>(f->ws.status.p), f->ws.stream);
+            CK(cudaMemcpyAsync(f->ws.h_status, f->ws.status.p, 8, cudaMemcpyDeviceToHost, f->ws.stream));
+            CK(cudaStreamSynchronize(f->ws.stream));
+            f->img.collision_base = f->ws.h_status[0];
+            lphb_info& i = f->info;
+            i.k = f->img.k;
+            i.m = f->img.m;
+            i.kmer_bits = uint32_t(kmer_bits);
+            i.device = device;
+            i.mm_seed = f->img.mm_seed;
+            i.nkmers = f->img.nkmers;
+            i.distinct_minimizers = f->img.distinct_minimizers;
+            i.n_maximal = f->img.n_maximal;
+            i.right_coll_sizes_start = f->img.right_start;
+            i.none_sizes_start = f->img.none_sizes_start;
+            i.none_pos_start = f->img.none_pos_start;
+            i.fallback_keys = builder.fallback_keys();
+            i.file_bytes = builder.file_bytes();
+            i.device_bytes = arena.size();
+        } catch (...) {
+            f->ws.destroy();
+            if (f->d_arena) cudaFree(f->d_arena);
+            delete f;
+            throw;
+        }
+        *out = f;
+        return LPHB_OK;
+    });
+}
+
+// main kernel bracketed by the handle's events (elapsed time is read lazily by lphb_mphf_stats)
+void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
+    CK(cudaEventRecord(f->ws.ev0, s));
+    if (!launch_query_tiled(f->img, b, s)) launch_query_generic(f->img, b, s);
+    CK(cudaEventRecord(f->ws.ev1, s));
+    f->events_pending = true;
+    launch_count_dirty(b.dirty, b.n_contigs, b.status, s);
+    f->stats.kernel_launches += 2;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lphb_last_error(void) { return g_err.c_str(); }
+const char* lphb_version(void) { return "lphash_b200 0.1 (sm_100a)"; }
+
+int lphb_device_count(int* count) {
+    if (!count) return fail(LPHB_E_ARG, "count is null");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(LPHB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    return LPHB_OK;
+}
+
+int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device,
+                          lphb_mphf** out) {
+    if (!image) return fail(LPHB_E_ARG, "image is null");
+    return load_image(static_cast<const uint8_t*>(image), nbytes, kmer_bits, device, out);
+}
+
+int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out) {
+    if (!path) return fail(LPHB_E_ARG, "path is null");
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in.good()) return fail(LPHB_E_IO, std::string("cannot open ") + path);
+    std::streamsize n = in.tellg();
+    in.seekg(0);
+    std::vector<uint8_t> buf(static_cast<size_t>(n));
+    if (n && !in.read(reinterpret_cast<char*>(buf.data()), n)) return fail(LPHB_E_IO, "short read");
+    return load_image(buf.data(), uint64_t(n), kmer_bits, device, out);
+}
+
+int lphb_mphf_free(lphb_mphf* f) {
+    if (!f) return LPHB_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(f->device);
+    f->ws.destroy();
+    if (f->d_arena) cudaFree(f->d_arena);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete f;
+    return LPHB_OK;
+}
+
+int lphb_mphf_info(const lphb_mphf* f, lphb_info* info) {
+    if (!f || !info) return fail(LPHB_E_ARG, "null argument");
+    *info = f->info;
+    return LPHB_OK;
+}
+
+int lphb_mphf_stats(const lphb_mphf* cf, lphb_stats* stats) {
+    if (!cf || !stats) return fail(LPHB_E_ARG, "null argument");
+    auto* f = const_cast<lphb_mphf*>(cf);
+    if (f->events_pending) {  // device time of the last main kernel (waits for it to finish)
+        float ms = 0;
+        if (cudaEventSynchronize(f->ws.ev1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, f->ws.ev0, f->ws.ev1) == cudaSuccess)
+            f->stats.kernel_ms = ms;
+        else
+            cudaGetLastError();
+        f->events_pending = false;
+    }
+    *stats = f->stats;
+    return LPHB_OK;
+}
+
+int lphb_host_alloc(void** ptr, uint64_t nbytes) {
+    if (!ptr) return fail(LPHB_E_ARG, "ptr is null");
+    cudaError_t e = cudaMallocHost(ptr, nbytes ? nbytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LPHB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    return LPHB_OK;
+}
+
+int lphb_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return LPHB_OK;
+}
+
+int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* d_offsets,
+                             const uint64_t* h_offsets, uint64_t n_contigs, uint64_t* d_codes,
+                             uint64_t codes_capacity, uint64_t* d_code_offsets, uint64_t* d_status,
+                             void* stream) {
+    if (!f || !d_offsets || !h_offsets || !d_code_offsets || !d_status)
+        return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(f->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        f->stats = lphb_stats{};
+        const uint32_t k = f->img.k;
+        uint64_t total = 0;
+        for (uint64_t c = 0; c < n_contigs; ++c) {
+            if (h_offsets[c + 1] < h_offsets[c]) return fail(LPHB_E_ARG, "offsets must be non-decreasing");
+            uint64_t len = h_offsets[c + 1] - h_offsets[c];
+            total += len >= k ? len - k + 1 : 0;
+        }
+        if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+        if (total && (!d_bases || !d_codes)) return fail(LPHB_E_ARG, "null data pointer");
+        Workspace& ws = f->ws;
+        ws.tmp.reserve(code_offsets_tmp_bytes(n_contigs));
+        ws.dirty.reserve(n_contigs + 8);
+        CK(cudaMemsetAsync(ws.dirty.p, 0, n_contigs + 8, s));
+        auto* st = reinterpret_cast<unsigned long long*>(d_status);
+        launch_code_offsets(d_offsets, n_contigs, k, d_code_offsets, st, ws.tmp.p, ws.tmp.cap, s);
+        f->stats.kernel_launches += 2;
+        DevBatch b{};
+        b.bases = d_bases;
+        b.offsets = d_offsets;
+        b.code_off = d_code_offsets;
+        b.n_contigs = n_contigs;
+        b.first_base = h_offsets[0];
+        b.end_base = h_offsets[n_contigs];
+        b.codes = d_codes;
+        b.dirty = ws.dirty.as<uint8_t>();
+        b.status = st;
+        if (n_contigs) run_kernels(f, b, s);
+        CK(cudaGetLastError());
+        return LPHB_OK;
+    });
+}
+
+int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                      uint64_t* codes, uint64_t codes_capacity, uint64_t* code_offsets,
+                      uint64_t* n_codes) {
+    if (!f || !offsets || !code_offsets || !n_codes) return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(f->device);
+        Workspace& ws = f->ws;
+        cudaStream_t s = ws.stream;
+        f->stats = lphb_stats{};
+        const uint32_t k = f->img.k, m = f->img.m;
+        // layout for clean input: L-k+1 codes per contig (partitioned_mphf.hpp:79-80)
+        uint64_t total = 0;
+        for (uint64_t c = 0; c < n_contigs; ++c) {
+            if (offsets[c + 1] < offsets[c]) return fail(LPHB_E_ARG, "offsets must be non-decreasing");
+            uint64_t len = offsets[c + 1] - offsets[c];
+            code_offsets[c] = total;
+            total += len >= k ? len - k + 1 : 0;
+        }
+        code_offsets[n_contigs] = total;
+        *n_codes = total;
+        if (n_contigs == 0) return LPHB_OK;
+        const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
+        if (span && !bases) return fail(LPHB_E_ARG, "bases is null");
+        ws.bases.reserve(span + 64);
+        ws.offsets.reserve((n_contigs + 1) * 8);
+        ws.code_off.reserve((n_contigs + 1) * 8);
+        ws.codes.reserve(total * 8 + 64);
+        ws.dirty.reserve(n_contigs + 8);
+        CK(cudaMemcpyAsync(ws.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ws.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ws.code_off.p, code_offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ws.dirty.p, 0, n_contigs + 8, s));
+        CK(cudaMemsetAsync(ws.status.p, 0, 4 * sizeof(unsigned long long), s));
+        f->stats.h2d_bytes = span + 2 * (n_contigs + 1) * 8;
+        DevBatch b{};
+        b.bases = ws.bases.as<char>() - first;  // kernels index bases[offsets[c] + ...]
+        b.offsets = ws.offsets.as<uint64_t>();
+        b.code_off = ws.code_off.as<uint64_t>();
+        b.n_contigs = n_contigs;
+        b.first_base = first;
+        b.end_base = first + span;
+        b.codes = ws.codes.as<uint64_t>();
+        b.dirty = ws.dirty.as<uint8_t>();
+        b.status = ws.status.as<unsigned long long>();
+        run_kernels(f, b, s);
+        CK(cudaMemcpyAsync(ws.h_status, ws.status.p, 4 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        const uint64_t n_dirty = ws.h_status[1];
+        f->stats.dirty_contigs = n_dirty;
+        if (n_dirty == 0) {
+            if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+            if (total) CK(cudaMemcpyAsync(codes, ws.codes.p, total * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            f->stats.d2h_bytes = total * 8 + 32;
+            return LPHB_OK;
+        }
+        // ---- contigs with non-ACGT bytes: exact sequential emulation ----------
+        std::vector<uint8_t> dirty(n_contigs);
+        CK(cudaMemcpy(dirty.data(), ws.dirty.p, n_contigs, cudaMemcpyDeviceToHost));
+        std::vector<uint64_t> list, q_off;
+        uint64_t q_total = 0;
+        for (uint64_t c = 0; c < n_contigs; ++c)
+            if (dirty[c]) {
+                uint64_t len = offsets[c + 1] - offsets[c];
+                list.push_back(c);
+                q_off.push_back(q_total);
+                q_total += len >= m ? len - m + 1 : 0;  // at most one code per m-mer
+            }
+        ws.aux0.reserve(list.size() * 8);
+        ws.aux1.reserve(list.size() * 8);
+        ws.aux2.reserve(list.size() * 8);
+        ws.codes2.reserve(q_total * 8 + 64);
+        CK(cudaMemcpyAsync(ws.aux0.p, list.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ws.aux1.p, q_off.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
+        launch_query_quirk(f->img, b.bases, b.offsets, ws.aux0.as<uint64_t>(), list.size(),
+                           ws.aux1.as<uint64_t>(), ws.codes2.as<uint64_t>(), ws.aux2.as<uint64_t>(), s);
+        f->stats.kernel_launches += 1;
+        std::vector<uint64_t> counts(list.size());
+        CK(cudaMemcpyAsync(counts.data(), ws.aux2.p, list.size() * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        // final layout + where each contig's codes come from (clean layout or quirk scratch)
+        std::vector<uint64_t> src_off(n_contigs);
+        uint64_t new_total = 0, clean_run = 0;
+        for (uint64_t c = 0, j = 0; c < n_contigs; ++c) {
+            uint64_t len = offsets[c + 1] - offsets[c];
+            uint64_t clean_cnt = len >= k ? len - k + 1 : 0;
+            uint64_t cnt = clean_cnt;
+            if (dirty[c]) {
+                src_off[c] = q_off[j];
+                cnt = counts[j++];
+            } else {
+                src_off[c] = clean_run;
+            }
+            clean_run += clean_cnt;
+            code_offsets[c] = new_total;
+            new_total += cnt;
+        }
+        code_offsets[n_contigs] = new_total;
+        *n_codes = new_total;
+        if (new_total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+        ws.aux3.reserve((n_contigs + 1) * 8);
+        ws.tmp.reserve(new_total * 8 + 64);
+        CK(cudaMemcpyAsync(ws.aux3.p, src_off.data(), n_contigs * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ws.code_off.p, code_offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
+        launch_assemble(ws.tmp.as<uint64_t>(), ws.code_off.as<uint64_t>(), ws.codes.as<uint64_t>(),
+                        ws.codes2.as<uint64_t>(), ws.aux3.as<uint64_t>(), ws.dirty.as<uint8_t>(),
+                        n_contigs, s);
+        f->stats.kernel_launches += 1;
+        if (new_total) CK(cudaMemcpyAsync(codes, ws.tmp.p, new_total * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        f->stats.d2h_bytes = new_total * 8 + n_contigs + list.size() * 8 + 32;
+        return LPHB_OK;
+    });
+}
+
+
+// ---- build-side scan ---------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Per-call device buffers of the scan pipeline (freed on scope exit).
+struct ScanSession {
+    DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, head_at, tmp, status;
+    cudaStream_t s = nullptr;
+    ScanBatch b{};
+    uint64_t n_records = 0, n_kmers = 0, tmp_bytes = 0;
+    ~ScanSession() {
+        for (DevBuf* d : {&bases, &offsets, &code_off, &id_base, &dirty, &head, &pos, &rank, &records,
+                          &head_at, &tmp, &status})
+            d->release();
+        if (s) cudaStreamDestroy(s);
+    }
+};
+
+// Passes 1-2 of the scan for a host batch; leaves records / rank / head_at on the device.
+int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+             const uint64_t* offsets, uint64_t n_contigs, uint64_t mm_count_in,
+             uint64_t* mm_count_out) {
+    if (m == 0 || m > 31 || k < m || k > 63) return fail(LPHB_E_ARG, "need 1 <= m <= 31, m <= k <= 63");
+    uint64_t n_kmers = 0, n_mmers = 0;
+    for (uint64_t c = 0; c < n_contigs; ++c) {
+        if (offsets[c + 1] < offsets[c]) return fail(LPHB_E_ARG, "offsets must be non-decreasing");
+        uint64_t len = offsets[c + 1] - offsets[c];
+        n_kmers += len >= k ? len - k + 1 : 0;
+        n_mmers += len >= m ? len - m + 1 : 0;
+    }
+    *mm_count_out = mm_count_in + n_mmers;
+    S.n_kmers = n_kmers;
+    S.n_records = 0;
+    if (n_kmers >= (1ull << 32)) return fail(LPHB_E_ARG, "batch holds >= 2^32 k-mers: split it");
+    CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
+    if (n_contigs == 0 || n_kmers == 0) return LPHB_OK;
+    if (!bases) return fail(LPHB_E_ARG, "bases is null");
+    cudaStream_t s = S.s;
+    const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
+    S.bases.reserve(span + 64);
+    S.offsets.reserve((n_contigs + 1) * 8);
+    S.code_off.reserve((n_contigs + 1) * 8);
+    S.id_base.reserve((n_contigs + 1) * 8);
+    S.dirty.reserve(n_contigs + 8);
+    S.head.reserve(n_kmers + 8);
+    S.pos.reserve(n_kmers + 8);
+    S.rank.reserve((n_kmers + 2) * 4);
+    S.status.reserve(64);
+    uint64_t t1 = head_ranks_tmp_bytes(n_kmers > n_contigs ? n_kmers : n_contigs);
+    uint64_t t2 = code_offsets_tmp_bytes(n_contigs);
+    uint64_t t3 = exclusive_u32_tmp_bytes(n_kmers);
+    S.tmp_bytes = t1 > t2 ? t1 : t2;
+    if (t3 > S.tmp_bytes) S.tmp_bytes = t3;
+    S.tmp.reserve(S.tmp_bytes);
+    CK(cudaMemcpyAsync(S.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(S.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(S.dirty.p, 0, n_contigs + 8, s));
+    CK(cudaMemsetAsync(S.head.p, 0, n_kmers + 8, s));
+    auto* st = S.status.as<unsigned long long>();
+    launch_code_offsets(S.offsets.as<uint64_t>(), n_contigs, k, S.code_off.as<uint64_t>(), st, S.tmp.p,
+                        S.tmp_bytes, s);
+    launch_id_base(S.offsets.as<uint64_t>(), n_contigs, m, mm_count_in, S.id_base.as<uint64_t>(),
+                   S.tmp.p, S.tmp_bytes, s);
+    ScanBatch& b = S.b;
+    b.bases = S.bases.as<char>() - first;
+    b.offsets = S.offsets.as<uint64_t>();
+    b.code_off = S.code_off.as<uint64_t>();
+    b.id_base = S.id_base.as<uint64_t>();
+    b.n_contigs = n_contigs;
+    b.first_base = first;
+    b.end_base = first + span;
+    b.n_kmers = n_kmers;
+    b.k = k;
+    b.m = m;
+    b.seed = seed;
+    b.dirty = S.dirty.as<uint8_t>();
+    launch_scan_heads(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), s);
+    launch_count_dirty(b.dirty, n_contigs, st, s);
+    launch_head_ranks(S.head.as<uint8_t>(), n_kmers, S.rank.as<uint32_t>(), S.tmp.p, S.tmp_bytes, s);
+    unsigned long long h_st[2] = {0, 0};
+    uint32_t n_rec32 = 0;
+    CK(cudaMemcpyAsync(h_st, st, sizeof(h_st), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&n_rec32, S.rank.as<uint32_t>() + n_kmers, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h_st[1] != 0)
+        return fail(LPHB_E_ARG,
+                    "build input contains non-ACGT bytes (the reference's build requires valid "
+                    "k-mers only, src/parser_build.cpp:13-16); not supported by the GPU scan yet");
+    S.n_records = n_rec32;
+    S.records.reserve(S.n_records * 18 + 64);
+    S.head_at.reserve((S.n_records + 1) * 4);
+    launch_scan_emit(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), S.rank.as<uint32_t>(),
+                     S.records.as<uint8_t>(), S.head_at.as<uint32_t>(), s);
+    launch_scan_sizes(S.head_at.as<uint32_t>(), S.n_records, n_kmers, S.records.as<uint8_t>(), s);
+    CK(cudaGetLastError());
+    return LPHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                         const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
+                         void* records, uint64_t records_capacity, uint64_t* n_records,
+                         uint64_t* n_kmers) {
+    if (!offsets || !mm_count || !n_records || !n_kmers) return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        ScanSession S;
+        uint64_t mm_out = *mm_count;
+        int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
+        if (rc != LPHB_OK) return rc;
+        *n_kmers = S.n_kmers;
+        *n_records = S.n_records;
+        if (S.n_records > records_capacity) return fail(LPHB_E_CAPACITY, "records buffer too small");
+        if (S.n_records) {
+            if (!records) return fail(LPHB_E_ARG, "records is null");
+            CK(cudaMemcpyAsync(records, S.records.p, S.n_records * 18, cudaMemcpyDeviceToHost, S.s));
+        }
+        CK(cudaStreamSynchronize(S.s));
+        *mm_count = mm_out;
+        return LPHB_OK;
+    });
+}
+
+int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                         const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
+                         const uint64_t* ids, uint64_t n_ids, int kmer_bits, void* kmers,
+                         uint64_t kmers_capacity, uint64_t* n_kmers) {
+    if (!offsets || !mm_count || !n_kmers || (n_ids && !ids)) return fail(LPHB_E_ARG, "null argument");
+    if (kmer_bits != 64 && kmer_bits != 128) return fail(LPHB_E_ARG, "kmer_bits must be 64 or 128");
+    if (k > uint32_t(kmer_bits / 2 - 1)) return fail(LPHB_E_ARG, "k too large for this kmer_t");
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        ScanSession S;
+        uint64_t mm_out = *mm_count;
+        int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
+        if (rc != LPHB_OK) return rc;
+        *n_kmers = 0;
+        if (S.n_records == 0 || n_ids == 0) {
+            *mm_count = mm_out;
+            return LPHB_OK;
+        }
+        DevBuf d_ids, take, out_off, out;
+        struct Free {
+            DevBuf *a, *b, *c, *d;
+            ~Free() { a->release(); b->release(); c->release(); d->release(); }
+        } freer{&d_ids, &take, &out_off, &out};
+        cudaStream_t s = S.s;
+        d_ids.reserve(n_ids * 8);
+        take.reserve((S.n_records + 1) * 4);
+        out_off.reserve((S.n_records + 1) * 8);
+        CK(cudaMemcpyAsync(d_ids.p, ids, n_ids * 8, cudaMemcpyHostToDevice, s));
+        launch_colliding_mark(S.records.as<uint8_t>(), S.n_records, d_ids.as<uint64_t>(), n_ids,
+                              take.as<uint32_t>(), s);
+        uint64_t tb = exclusive_u32_tmp_bytes(S.n_records);
+        S.tmp.reserve(tb);
+        launch_exclusive_u32(take.as<uint32_t>(), S.n_records, out_off.as<uint64_t>(), S.tmp.p, tb, s);
+        uint64_t total = 0;
+        CK(cudaMemcpyAsync(&total, out_off.as<uint64_t>() + S.n_records, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *n_kmers = total;
+        if (total > kmers_capacity) return fail(LPHB_E_CAPACITY, "kmers buffer too small");
+        if (total) {
+            if (!kmers) return fail(LPHB_E_ARG, "kmers is null");
+            const uint64_t bytes = total * uint64_t(kmer_bits / 8);
+            out.reserve(bytes + 64);
+            launch_colliding_emit(S.b, S.rank.as<uint32_t>(), S.head_at.as<uint32_t>(),
+                                  take.as<uint32_t>(), out_off.as<uint64_t>(), kmer_bits,
+                                  out.as<uint8_t>(), s);
+            CK(cudaMemcpyAsync(kmers, out.p, bytes, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            CK(cudaGetLastError());
+        }
+        *mm_count = mm_out;
+        return LPHB_OK;
+    });
+}
+
+}  // extern "C"

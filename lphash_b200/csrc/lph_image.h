@@ -1,0 +1,58 @@
+// Host side of the device image: parses the serialized lphash::mphf (`.lph`) and lays the arrays
+// out in one arena that is uploaded with a single copy.
+//
+// File format (little-endian, essentials visitor: PODs raw, vector<T> = u64 n + n*sizeof(T)):
+//   u8 k, u8 m, u64 mm_seed, nkmers, distinct_minimizers, n_maximal, right_coll_sizes_start,
+//   none_sizes_start, none_pos_start            ref include/partitioned_mphf.hpp:204-211
+//   single_phf minimizer_order                  ref pthash/include/single_phf.hpp:88-97
+//   quartet_wtree {root, left_right, max_none}  ref include/quartet_wtree.hpp:43-48,
+//                                                   include/rs_bit_vector.hpp:91-96
+//   ef_sequence sizes_and_positions             ref include/ef_sequence.hpp:107-112
+//   single_phf fallback_kmer_order
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "device_image.h"
+
+namespace lphb {
+
+struct FormatError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// Arena under construction: every array is appended 256-byte aligned; device pointers in the
+// DevImage are stored as byte offsets first and rebased once the arena is on the device.
+class ImageBuilder {
+public:
+    // Parses `data[0..n)`; throws FormatError.  After this, image() holds offsets-as-pointers.
+    void parse(const uint8_t* data, uint64_t n, int kmer_bits);
+    std::vector<uint8_t> const& arena() const { return arena_; }
+    // Returns the image with every pointer rebased onto `device_base`.
+    DevImage rebased(const void* device_base) const;
+    uint64_t fallback_keys() const { return fallback_keys_; }
+    uint64_t file_bytes() const { return file_bytes_; }
+
+private:
+    struct Cursor;
+    template <class T>
+    const T* append(const T* src, uint64_t n, uint64_t pad_elems = 0);
+    void read_compact(Cursor& c, DevCompact& out);
+    void read_ef(Cursor& c, DevEF& out);
+    void read_rank(Cursor& c, DevRank& out);
+    void read_phf(Cursor& c, DevPhf& out);
+    static void rebase_compact(DevCompact& c, const uint8_t* base);
+    static void rebase_ef(DevEF& e, const uint8_t* base);
+    static void rebase_phf(DevPhf& p, const uint8_t* base);
+
+    std::vector<uint8_t> arena_;
+    DevImage img_{};
+    uint64_t fallback_keys_ = 0, file_bytes_ = 0;
+};
+
+// ceil(2^96 / d) as three 32-bit limbs (d >= 1, d < 2^32); limbs all zero for d == 1.
+void reciprocal96(uint64_t d, uint32_t out[3]);
+
+}  // namespace lphb

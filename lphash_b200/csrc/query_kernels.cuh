@@ -1,0 +1,56 @@
+// Launchers of the query kernels (query_generic.cu, query_tiled.cu).  All pointers are device
+// pointers; all launches are asynchronous on `stream`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_image.h"
+
+namespace lphb {
+
+// Per-batch device-side description of the contig layout.
+struct DevBatch {
+    const char* bases;          // concatenated ASCII
+    const uint64_t* offsets;    // n_contigs + 1, indexes `bases`
+    const uint64_t* code_off;   // n_contigs + 1: exclusive scan of max(0, L - k + 1)
+    uint64_t n_contigs;
+    uint64_t first_base;        // offsets[0]
+    uint64_t end_base;          // offsets[n_contigs]
+    uint64_t* codes;            // output
+    uint8_t* dirty;             // n_contigs flags: contig contains a non-ACGT byte
+    unsigned long long* status; // [0] unused here, [1] += number of dirty contigs
+};
+
+// code_off[c] = sum_{c' < c} max(0, L_c' - k + 1); status[0] = total.  One launch, any n.
+void launch_code_offsets(const uint64_t* d_offsets, uint64_t n_contigs, uint32_t k,
+                         uint64_t* d_code_off, unsigned long long* d_status, void* d_tmp,
+                         uint64_t tmp_bytes, cudaStream_t stream);
+uint64_t code_offsets_tmp_bytes(uint64_t n_contigs);
+
+// Generic kernel: any (k, m); one thread per k-mer, everything recomputed per k-mer.
+void launch_query_generic(DevImage const& img, DevBatch const& b, cudaStream_t stream);
+
+// Tiled kernel for the (k, m) pairs it is instantiated for; returns false if (k, m) is not one
+// of them (the caller then uses the generic kernel).
+bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream);
+
+// Exact sequential emulation of the reference's streaming loop for contigs that contain
+// non-ACGT bytes (one thread per listed contig).  out_off[j] = where contig list[j] may write
+// (capacity L - m + 1 each); counts[j] receives how many codes it produced.
+void launch_query_quirk(DevImage const& img, const char* bases, const uint64_t* offsets,
+                        const uint64_t* list, uint64_t n_list, const uint64_t* out_off,
+                        uint64_t* out, uint64_t* counts, cudaStream_t stream);
+
+// dst[dst_off[c] .. +cnt[c]) = src_c[src_off[c] ..) where src_c = from_b[c] ? src_b : src_a.
+void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src_a,
+                     const uint64_t* src_b, const uint64_t* src_off, const uint8_t* from_b,
+                     uint64_t n_contigs, cudaStream_t stream);
+
+// status[1] += number of set flags in dirty[0..n)
+void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status,
+                        cudaStream_t stream);
+
+// One-thread kernel computing collision_base = EF[none_pos_start] + w * n_maximal.
+void launch_collision_base(DevImage const& img, uint64_t* d_out, cudaStream_t stream);
+
+}  // namespace lphb

@@ -1,0 +1,318 @@
+// Build-side scan, generic form (any k, m): the stateless definition of the record stream that
+// minimizer::from_string emits (SURVEY.md S2'; ref include/minimizer.hpp:11-170):
+//   for k-mer i of a contig, b(i) = leftmost argmin of the m-mer hash over offsets i..i+w-1;
+//   a record starts at every i with b(i) != b(i-1) (and at the contig's first k-mer);
+//   record = {itself = m-mer at b, id = id_base(contig) + b, p1 = b - i, size = run length}.
+// and of minimizer::get_colliding_kmers (ref include/minimizer.hpp:172-319): the forward k-mers
+// of every record whose id is in the sorted id list, in scan order.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "device_mphf.cuh"
+#include "scan_kernels.cuh"
+
+namespace lphb {
+
+namespace {
+
+struct MmerCount {
+    const uint64_t* offsets;
+    uint32_t m;
+    __host__ __device__ uint64_t operator()(uint64_t c) const {
+        uint64_t len = offsets[c + 1] - offsets[c];
+        return len >= m ? len - m + 1 : 0;
+    }
+};
+
+struct AddBase {
+    uint64_t base;
+    __host__ __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a + b; }
+};
+
+__global__ void k_finish_id_base(const uint64_t* offsets, uint64_t n, uint32_t m, uint64_t mm_in,
+                                 uint64_t* id_base) {
+    // ExclusiveSum filled id_base[0..n) with sums starting at 0: shift by mm_in is folded into the
+    // scan's initial value; only the closing entry is written here.
+    uint64_t total = mm_in;
+    if (n) {
+        uint64_t len = offsets[n] - offsets[n - 1];
+        total = id_base[n - 1] + (len >= m ? len - m + 1 : 0);
+    }
+    id_base[n] = total;
+}
+
+__device__ __forceinline__ uint64_t find_contig(const uint64_t* offsets, uint64_t n, uint64_t i) {
+    uint64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// m-mer starting at base j (first base most significant), or false if a byte is invalid
+__device__ __forceinline__ bool read_mmer(const char* s, uint32_t m, uint64_t& out) {
+    uint64_t v = 0;
+    for (uint32_t j = 0; j < m; ++j) {
+        uint32_t code = nt4(uint8_t(s[j]));
+        if (code > 3) return false;
+        v = (v << 2) | code;
+    }
+    out = v;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_scan_heads(const __grid_constant__ ScanBatch b,
+                                                    uint8_t* head, uint8_t* pos) {
+    const uint32_t k = b.k, m = b.m, w = k - m + 1;
+    const uint64_t mm_mask = (uint64_t(1) << (2 * m)) - 1;
+    uint64_t span = b.end_base - b.first_base;
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < span;
+         t += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t i = b.first_base + t;
+        uint64_t c = find_contig(b.offsets, b.n_contigs, i);
+        uint64_t start = __ldg(b.offsets + c), end = __ldg(b.offsets + c + 1);
+        if (i + k > end) continue;
+        bool first = (i == start);
+        // rolling m-mers over bases [i - 1, i + k): w + 1 hashes (the extra one is the m-mer that
+        // left the window, needed for b(i-1))
+        uint64_t from = first ? i : i - 1;
+        uint64_t mm = 0;
+        bool ok = true;
+        uint64_t prev_best = 0, best = 0;
+        uint32_t prev_p = 0, best_p = 0;  // offsets relative to i - 1 (prev) and i (cur)
+        uint32_t run = 0;
+        for (uint64_t j = from; j < i + k; ++j) {
+            uint32_t code = nt4(uint8_t(b.bases[j]));
+            if (code > 3) { ok = false; break; }
+            mm = ((mm << 2) | code) & mm_mask;
+            if (++run < m) continue;
+            uint64_t q = j + 1 - m;  // start of this m-mer
+            uint64_t h = murmur64(mm, b.seed);
+            if (q >= i) {            // in the current window [i, i+w)
+                if (q == i || h < best) { best = h; best_p = uint32_t(q - i); }
+            }
+            if (!first && q < i + w - 1) {  // in the previous window [i-1, i+w-1)
+                if (q == i - 1 || h < prev_best) { prev_best = h; prev_p = uint32_t(q - (i - 1)); }
+            }
+        }
+        if (!ok) {
+            b.dirty[c] = 1;
+            continue;
+        }
+        uint64_t d = __ldg(b.code_off + c) + (i - start);
+        bool is_head = first || (uint64_t(best_p) + i != uint64_t(prev_p) + i - 1);
+        head[d] = is_head ? 1 : 0;
+        pos[d] = uint8_t(best_p);
+    }
+}
+
+struct U8ToU32 {
+    __host__ __device__ uint32_t operator()(uint8_t v) const { return v; }
+};
+
+__global__ void k_finish_ranks(const uint8_t* head, uint64_t n, uint32_t* rank) {
+    rank[n] = n ? rank[n - 1] + head[n - 1] : 0;
+}
+
+__device__ __forceinline__ void store_record(uint8_t* rec, uint64_t itself, uint64_t id, uint8_t p1) {
+    // 18-byte packed mm_record_t (constants.hpp:26-33); records are only 2-byte aligned
+    uint16_t* q = reinterpret_cast<uint16_t*>(rec);
+    q[0] = uint16_t(itself); q[1] = uint16_t(itself >> 16); q[2] = uint16_t(itself >> 32); q[3] = uint16_t(itself >> 48);
+    q[4] = uint16_t(id); q[5] = uint16_t(id >> 16); q[6] = uint16_t(id >> 32); q[7] = uint16_t(id >> 48);
+    rec[16] = p1;
+}
+
+__global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanBatch b,
+                                                   const uint8_t* head, const uint8_t* pos,
+                                                   const uint32_t* rank, uint8_t* records,
+                                                   uint32_t* head_at) {
+    const uint32_t k = b.k, m = b.m;
+    uint64_t span = b.end_base - b.first_base;
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < span;
+         t += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t i = b.first_base + t;
+        uint64_t c = find_contig(b.offsets, b.n_contigs, i);
+        uint64_t start = __ldg(b.offsets + c), end = __ldg(b.offsets + c + 1);
+        if (i + k > end || b.dirty[c]) continue;
+        uint64_t d = __ldg(b.code_off + c) + (i - start);
+        if (!head[d]) continue;
+        uint32_t r = rank[d];
+        uint64_t bpos = i + pos[d];
+        uint64_t mm = 0;
+        read_mmer(b.bases + bpos, m, mm);
+        store_record(records + 18ull * r, mm, __ldg(b.id_base + c) + (bpos - start), pos[d]);
+        head_at[r] = uint32_t(d);
+    }
+}
+
+__global__ void k_scan_sizes(const uint32_t* head_at, uint64_t n_records, uint64_t n_kmers,
+                             uint8_t* records) {
+    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < n_records;
+         r += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t next = r + 1 < n_records ? head_at[r + 1] : n_kmers;
+        records[18 * r + 17] = uint8_t(next - head_at[r]);
+    }
+}
+
+__device__ __forceinline__ uint64_t load_u64_2(const uint8_t* p) {
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    return uint64_t(q[0]) | (uint64_t(q[1]) << 16) | (uint64_t(q[2]) << 32) | (uint64_t(q[3]) << 48);
+}
+
+__global__ void k_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
+                                 uint64_t n_ids, uint32_t* take) {
+    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < n_records;
+         r += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t id = load_u64_2(records + 18 * r + 8);
+        uint64_t lo = 0, hi = n_ids;  // first index with ids[idx] >= id
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(ids + mid) < id) lo = mid + 1; else hi = mid;
+        }
+        bool in = lo < n_ids && __ldg(ids + lo) == id;
+        take[r] = in ? uint32_t(records[18 * r + 17]) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_colliding_emit(const __grid_constant__ ScanBatch b,
+                                                        const uint32_t* rank,
+                                                        const uint32_t* head_at,
+                                                        const uint32_t* take,
+                                                        const uint64_t* out_off, int kmer_bits,
+                                                        uint8_t* kmers) {
+    const uint32_t k = b.k;
+    uint64_t span = b.end_base - b.first_base;
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < span;
+         t += uint64_t(gridDim.x) * blockDim.x) {
+        uint64_t i = b.first_base + t;
+        uint64_t c = find_contig(b.offsets, b.n_contigs, i);
+        uint64_t start = __ldg(b.offsets + c), end = __ldg(b.offsets + c + 1);
+        if (i + k > end || b.dirty[c]) continue;
+        uint64_t d = __ldg(b.code_off + c) + (i - start);
+        uint32_t r = rank[d + 1] - 1;  // record containing k-mer d (heads before or at d, minus 1)
+        if (!take[r]) continue;
+        uint64_t lo = 0, hi = 0;
+        for (uint32_t j = 0; j < k; ++j) {
+            uint32_t code = nt4(uint8_t(b.bases[i + j]));
+            hi = (hi << 2) | (lo >> 62);
+            lo = (lo << 2) | (code & 3);
+        }
+        uint64_t o = out_off[r] + (d - head_at[r]);
+        if (kmer_bits == 64) {
+            reinterpret_cast<uint64_t*>(kmers)[o] = lo;
+        } else {
+            reinterpret_cast<uint64_t*>(kmers)[2 * o] = lo;
+            reinterpret_cast<uint64_t*>(kmers)[2 * o + 1] = hi;
+        }
+    }
+}
+
+unsigned grid_for(uint64_t n, unsigned cap_blocks = 148 * 64) {
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    return unsigned(blocks);
+}
+
+}  // namespace
+
+void launch_id_base(const uint64_t* d_offsets, uint64_t n_contigs, uint32_t m, uint64_t mm_count_in,
+                    uint64_t* d_id_base, void* d_tmp, uint64_t tmp_bytes, cudaStream_t stream) {
+    if (n_contigs) {
+        MmerCount op{d_offsets, m};
+        cub::CountingInputIterator<uint64_t> cnt(0);
+        cub::TransformInputIterator<uint64_t, MmerCount, cub::CountingInputIterator<uint64_t>> it(cnt, op);
+        size_t bytes = tmp_bytes;
+        cub::DeviceScan::ExclusiveScan(d_tmp, bytes, it, d_id_base, AddBase{0}, mm_count_in, n_contigs,
+                                       stream);
+    }
+    k_finish_id_base<<<1, 1, 0, stream>>>(d_offsets, n_contigs, m, mm_count_in, d_id_base);
+}
+
+void launch_scan_heads(ScanBatch const& b, uint8_t* head, uint8_t* pos, cudaStream_t stream) {
+    uint64_t span = b.end_base - b.first_base;
+    if (!span) return;
+    k_scan_heads<<<grid_for(span), 256, 0, stream>>>(b, head, pos);
+}
+
+uint64_t head_ranks_tmp_bytes(uint64_t n_kmers) {
+    size_t bytes = 0;
+    cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(nullptr, U8ToU32{});
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, n_kmers);
+    size_t bytes2 = 0;
+    MmerCount op{nullptr, 1};
+    cub::CountingInputIterator<uint64_t> cnt(0);
+    cub::TransformInputIterator<uint64_t, MmerCount, cub::CountingInputIterator<uint64_t>> it2(cnt, op);
+    cub::DeviceScan::ExclusiveScan(nullptr, bytes2, it2, (uint64_t*)nullptr, AddBase{0}, uint64_t(0), n_kmers);
+    return (bytes > bytes2 ? bytes : bytes2) + 256;
+}
+
+void launch_head_ranks(const uint8_t* head, uint64_t n_kmers, uint32_t* rank, void* d_tmp,
+                       uint64_t tmp_bytes, cudaStream_t stream) {
+    if (n_kmers) {
+        cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(head, U8ToU32{});
+        size_t bytes = tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(d_tmp, bytes, it, rank, n_kmers, stream);
+    }
+    k_finish_ranks<<<1, 1, 0, stream>>>(head, n_kmers, rank);
+}
+
+void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
+                      const uint32_t* rank, uint8_t* records, uint32_t* head_at, cudaStream_t stream) {
+    uint64_t span = b.end_base - b.first_base;
+    if (!span) return;
+    k_scan_emit<<<grid_for(span), 256, 0, stream>>>(b, head, pos, rank, records, head_at);
+}
+
+void launch_scan_sizes(const uint32_t* head_at, uint64_t n_records, uint64_t n_kmers,
+                       uint8_t* records, cudaStream_t stream) {
+    if (!n_records) return;
+    k_scan_sizes<<<grid_for(n_records), 256, 0, stream>>>(head_at, n_records, n_kmers, records);
+}
+
+void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
+                           uint64_t n_ids, uint32_t* take, cudaStream_t stream) {
+    if (!n_records) return;
+    k_colliding_mark<<<grid_for(n_records), 256, 0, stream>>>(records, n_records, ids, n_ids, take);
+}
+
+namespace {
+struct U32ToU64 {
+    __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
+};
+}  // namespace
+
+uint64_t exclusive_u32_tmp_bytes(uint64_t n) {
+    size_t bytes = 0;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(nullptr, U32ToU64{});
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (uint64_t*)nullptr, n);
+    return bytes + 256;
+}
+
+namespace {
+__global__ void k_finish_u32(const uint32_t* in, uint64_t n, uint64_t* out) {
+    out[n] = n ? out[n - 1] + in[n - 1] : 0;
+}
+}  // namespace
+
+void launch_exclusive_u32(const uint32_t* in, uint64_t n, uint64_t* out, void* d_tmp,
+                          uint64_t tmp_bytes, cudaStream_t stream) {
+    if (n) {
+        cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t*> it(in, U32ToU64{});
+        size_t bytes = tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(d_tmp, bytes, it, out, n, stream);
+    }
+    k_finish_u32<<<1, 1, 0, stream>>>(in, n, out);
+}
+
+void launch_colliding_emit(ScanBatch const& b, const uint32_t* rank, const uint32_t* head_at,
+                           const uint32_t* take, const uint64_t* out_off, int kmer_bits,
+                           uint8_t* kmers, cudaStream_t stream) {
+    uint64_t span = b.end_base - b.first_base;
+    if (!span) return;
+    k_colliding_emit<<<grid_for(span), 256, 0, stream>>>(b, rank, head_at, take, out_off, kmer_bits, kmers);
+}
+
+}  // namespace lphb

@@ -1,0 +1,66 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_NAMES = ["k31_m20_u64", "k31_m16_u128", "k63_m24_u128", "k47_m20_u128", "k15_m7_u64",
+                "k21_m11_u64"]
+REF_DATA = "/root/reference/data"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+class Golden:
+    """One committed fixture generated from the reference by tools/make_golden.py."""
+
+    def __init__(self, name):
+        self.name = name
+        self.lph = os.path.join(GOLDEN_DIR, name + ".lph")
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.z = z
+        self.k, self.m, self.bits = int(z["k"]), int(z["m"]), int(z["bits"])
+
+    def __getattr__(self, key):
+        return self.z[key]
+
+    def contigs(self):
+        raw = self.z["q_bases"].tobytes()
+        off = self.z["q_offsets"]
+        return [raw[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+    def is_clean(self):
+        """per query contig: ACGT/acgt/U/u only"""
+        ok = np.zeros(256, dtype=bool)
+        for ch in b"ACGTUacgtu":
+            ok[ch] = True
+        return [bool(ok[np.frombuffer(c, dtype=np.uint8)].all()) for c in self.contigs()]
+
+
+_cache = {}
+
+
+def load_golden(name):
+    if name not in _cache:
+        _cache[name] = Golden(name)
+    return _cache[name]
+
+
+@pytest.fixture(params=GOLDEN_NAMES)
+def golden(request):
+    return load_golden(request.param)
+
+
+def fnv_fold(codes) -> int:
+    """64-bit FNV-1a-style fold over u64 codes."""
+    h = 0xCBF29CE484222325
+    for v in np.asarray(codes, dtype=np.uint64).tolist():
+        h = ((h ^ v) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h

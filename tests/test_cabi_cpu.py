@@ -1,0 +1,89 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol the header declares,
+rejects malformed images before touching CUDA, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from lphash_b200 import api
+
+HEADER = os.path.join(ROOT, "include", "lphash_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lphb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(api.EXPORTS) == names
+
+
+def test_version_and_error_string():
+    L = api.lib()
+    assert b"sm_100a" in L.lphb_version()
+    assert isinstance(L.lphb_last_error(), bytes)
+
+
+def _load_bytes(image: bytes, bits=64):
+    h = C.c_void_p()
+    buf = (C.c_char * max(len(image), 1)).from_buffer_copy(image or b"\0")
+    rc = api.lib().lphb_mphf_load_memory(C.addressof(buf), len(image), bits, 0, C.byref(h))
+    return rc, h
+
+
+def test_missing_file_is_io_error():
+    h = C.c_void_p()
+    rc = api.lib().lphb_mphf_load_file(b"/nonexistent/x.lph", 64, 0, C.byref(h))
+    assert rc == api.E_IO and not h.value
+
+
+@pytest.mark.parametrize("name", ["k31_m20_u64", "k63_m24_u128"])
+def test_malformed_images_are_format_errors(name):
+    g = load_golden(name)
+    image = open(g.lph, "rb").read()
+    for bad in (image[:-1], image[: len(image) // 2], image[:40], image + b"\0", b""):
+        rc, h = _load_bytes(bad, g.bits)
+        assert rc == api.E_FORMAT, api.lib().lphb_last_error()
+        assert not h.value
+    # k too large for a 64-bit kmer_t
+    if g.k > 31:
+        rc, h = _load_bytes(image, 64)
+        assert rc == api.E_FORMAT
+    rc, h = _load_bytes(image, 32)
+    assert rc == api.E_FORMAT
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """On a box without a CUDA device a well-formed image must fail with E_CUDA."""
+    n = C.c_int(-1)
+    rc = api.lib().lphb_device_count(C.byref(n))
+    if rc == api.OK and n.value > 0:
+        pytest.skip("a GPU is present")
+    g = load_golden("k31_m20_u64")
+    with pytest.raises(api.LphashError) as e:
+        api.Mphf.load(g.lph, g.bits)
+    assert e.value.code == api.E_CUDA
+    with pytest.raises(api.LphashError) as e:
+        api.scan_superkmers(g.index_bases, g.index_offsets, g.k, g.m)
+    assert e.value.code == api.E_CUDA
+
+
+def test_argument_errors():
+    L = api.lib()
+    assert L.lphb_mphf_load_file(None, 64, 0, None) == api.E_ARG
+    assert L.lphb_mphf_info(None, None) == api.E_ARG
+    nrec, nk, mm = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    off = np.zeros(1, dtype=np.uint64)
+    rc = L.lphb_scan_superkmers(0, 31, 40, 42, None, off.ctypes.data, 0, C.byref(mm), None, 0,
+                                C.byref(nrec), C.byref(nk))
+    assert rc in (api.E_ARG, api.E_CUDA)

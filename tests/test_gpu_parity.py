@@ -1,0 +1,176 @@
+"""Parity of the CUDA path (through the C ABI, lphash_b200/liblphash_b200.so) with the reference:
+against the committed golden vectors generated from the unmodified reference, and against the
+CPU oracle on seeded inputs.  Bit-exact (integer work, zero tolerance)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+from lphash_b200 import api, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handles():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            g = load_golden(name)
+            cache[name] = api.Mphf.load(g.lph, g.bits)
+        return cache[name]
+
+    yield get
+    for h in cache.values():
+        h.close()
+
+
+def test_device_present():
+    assert api.device_count() >= 1
+
+
+def test_info_matches_file(golden, handles):
+    f = handles(golden.name)
+    o = oracle.OracleMphf(golden.lph, golden.bits)
+    assert (f.k, f.m, f.kmer_bits) == (golden.k, golden.m, golden.bits)
+    assert f.get_kmer_count() == o.info["nkmers"]
+    assert f.get_minimizer_L0() == o.info["distinct_minimizers"]
+    for a, b in [("n_maximal", "n_maximal"), ("right_coll_sizes_start", "right_coll_sizes_start"),
+                 ("none_sizes_start", "none_sizes_start"), ("none_pos_start", "none_pos_start"),
+                 ("fallback_keys", "fb_num_keys"), ("file_bytes", "file_bytes")]:
+        assert getattr(f.info, a) == o.info[b]
+
+
+def test_query_batch_matches_reference_golden(golden, handles):
+    """Whole query batch: members, non-members, short/empty contigs, lower case, and contigs with
+    non-ACGT bytes (reference streaming quirk reproduced exactly)."""
+    f = handles(golden.name)
+    codes, code_off = f.query_batch(golden.q_bases, golden.q_offsets)
+    assert np.array_equal(code_off, golden.q_code_offsets)
+    assert np.array_equal(codes, golden.q_codes)
+    assert f.stats().dirty_contigs == sum(1 for c in golden.is_clean() if not c)
+
+
+def test_single_contig_calls_match(golden, handles):
+    """operator()(contig, len) one contig at a time, like the reference driver (query.cpp:52)."""
+    f = handles(golden.name)
+    off = golden.q_code_offsets
+    contigs = golden.contigs()
+    for i in list(range(0, 12)) + list(range(len(contigs) - 60, len(contigs))):
+        want = golden.q_codes[int(off[i]):int(off[i + 1])]
+        got = f(contigs[i])
+        assert np.array_equal(got, want), i
+
+
+def test_clean_batch_has_no_dirty_contigs_and_is_perfect(golden, handles):
+    f = handles(golden.name)
+    codes, code_off = f.query_batch(golden.index_bases, golden.index_offsets)
+    n = f.get_kmer_count()
+    assert f.stats().dirty_contigs == 0
+    assert len(codes) == n
+    assert np.array_equal(np.sort(codes), np.arange(n, dtype=np.uint64))  # minimal perfect
+
+
+def test_offsets_not_starting_at_zero(golden, handles):
+    f = handles(golden.name)
+    skip = 5
+    codes, code_off = f.query_batch(golden.q_bases, golden.q_offsets[skip:])
+    base = int(golden.q_code_offsets[skip])
+    assert np.array_equal(codes, golden.q_codes[base:])
+    assert np.array_equal(code_off, golden.q_code_offsets[skip:] - np.uint64(base))
+
+
+@pytest.mark.parametrize("name", ["k31_m20_u64", "k63_m24_u128", "k15_m7_u64"])
+def test_random_reads_match_oracle(name, handles):
+    g = load_golden(name)
+    f = handles(name)
+    o = oracle.OracleMphf(g.lph, g.bits)
+    genome = g.index_bases[: int(g.index_offsets[10])]
+    bases, offsets = synth.reads(3000, genome, read_len=100 + g.k, seed=0xBEEF + g.k)
+    want, want_off = o.query_batch(bases, offsets)
+    got, got_off = f.query_batch(bases, offsets)
+    assert np.array_equal(got_off, want_off)
+    assert np.array_equal(got, want)
+
+
+def test_capacity_error(handles):
+    g = load_golden("k31_m20_u64")
+    f = handles(g.name)
+    out = np.empty(10, dtype=np.uint64)
+    with pytest.raises(api.LphashError) as e:
+        f.query_batch(g.index_bases, g.index_offsets, out=out)
+    assert e.value.code == api.E_CAPACITY
+
+
+def test_device_resident_variant(handles):
+    torch = pytest.importorskip("torch")
+    g = load_golden("k31_m20_u64")
+    f = handles(g.name)
+    dev = torch.device("cuda:0")
+    d_bases = torch.from_numpy(g.index_bases.copy()).to(dev)
+    offs = g.index_offsets.astype(np.int64)
+    d_off = torch.from_numpy(offs).to(dev)
+    n = len(offs) - 1
+    total = int(np.maximum(np.diff(offs) - g.k + 1, 0).sum())
+    d_codes = torch.empty(total, dtype=torch.int64, device=dev)
+    d_code_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    f.query_device(d_bases.data_ptr(), d_off.data_ptr(), g.index_offsets, d_codes.data_ptr(), total,
+                   d_code_off.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    status = d_status.cpu().numpy()
+    assert status[0] == total and status[1] == 0
+    want, want_off = f.query_batch(g.index_bases, g.index_offsets)
+    assert np.array_equal(d_codes.cpu().numpy().view(np.uint64), want)
+    assert np.array_equal(d_code_off.cpu().numpy().view(np.uint64), want_off)
+
+
+# ---- build-side scan ---------------------------------------------------------------------------
+
+def test_scan_matches_reference_golden(golden):
+    rec, nk, mm = api.scan_superkmers(golden.index_bases, golden.index_offsets, golden.k, golden.m)
+    assert nk == int(golden.n_kmers) and mm == int(golden.mm_count)
+    assert rec.dtype == golden.rec.dtype
+    assert np.array_equal(rec, golden.rec)
+
+
+def test_scan_mm_count_carries_over(golden):
+    """mm_count is in/out: scanning the set in two batches gives the same stream."""
+    off = golden.index_offsets
+    half = (len(off) - 1) // 2
+    r1, k1, mm1 = api.scan_superkmers(golden.index_bases, off[: half + 1], golden.k, golden.m)
+    r2, k2, mm2 = api.scan_superkmers(golden.index_bases, off[half:], golden.k, golden.m, mm_count=mm1)
+    assert k1 + k2 == int(golden.n_kmers) and mm2 == int(golden.mm_count)
+    assert np.array_equal(np.concatenate([r1, r2]), golden.rec)
+
+
+def test_scan_short_contigs(golden):
+    k, m = golden.k, golden.m
+    rng = np.random.Generator(np.random.PCG64(7))
+    lens = [0, 1, m - 1, m, k - 1, k, k + 1, 3 * k, 0, 5]
+    recs = [synth.random_bases(n, rng).tobytes() for n in lens]
+    bases = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    want, wk, wmm = oracle.scan(bases, offsets, k, m, mode=0)
+    got, gk, gmm = api.scan_superkmers(bases, offsets, k, m)
+    assert (gk, gmm) == (wk, wmm)
+    assert np.array_equal(got, want)
+
+
+def test_colliding_kmers_match_reference_golden(golden):
+    km = api.colliding_kmers(golden.index_bases, golden.index_offsets, golden.k, golden.m,
+                             golden.coll_ids, kmer_bits=golden.bits)
+    assert km.shape == golden.coll_kmers.shape
+    assert np.array_equal(km, golden.coll_kmers)
+
+
+def test_scan_then_classify_feeds_the_same_keys(golden):
+    """The GPU scan's stream, pushed through classify, yields the key stream PTHash consumes."""
+    rec, _, _ = api.scan_superkmers(golden.index_bases, golden.index_offsets, golden.k, golden.m)
+    trip, ids = oracle.classify(rec)
+    assert np.array_equal(trip, golden.triplets)
+    assert np.array_equal(ids, golden.coll_ids)
