@@ -59,7 +59,7 @@ struct DevBuf {
 };
 
 struct Workspace {
-    DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2;
+    DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
     unsigned long long* h_status = nullptr;  // pinned, 4 words
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -72,7 +72,7 @@ struct Workspace {
     }
     void destroy() {
         for (DevBuf* b : {&bases, &offsets, &code_off, &codes, &dirty, &status, &tmp, &aux0, &aux1,
-                          &aux2, &aux3, &codes2})
+                          &aux2, &aux3, &codes2, &tile})
             b->release();
         if (h_status) cudaFreeHost(h_status);
         if (ev0) cudaEventDestroy(ev0);
@@ -312,6 +312,9 @@ int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* 
         b.codes = d_codes;
         b.dirty = ws.dirty.as<uint8_t>();
         b.status = st;
+        ws.tile.reserve(query_tiled_ws_bytes(b.end_base - b.first_base));
+        b.tile_ws = ws.tile.p;
+        b.tile_ws_bytes = ws.tile.cap;
         if (n_contigs) run_kernels(f, b, s);
         CK(cudaGetLastError());
         return LPHB_OK;
@@ -362,6 +365,9 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         b.codes = ws.codes.as<uint64_t>();
         b.dirty = ws.dirty.as<uint8_t>();
         b.status = ws.status.as<unsigned long long>();
+        ws.tile.reserve(query_tiled_ws_bytes(span));
+        b.tile_ws = ws.tile.p;
+        b.tile_ws_bytes = ws.tile.cap;
         run_kernels(f, b, s);
         CK(cudaMemcpyAsync(ws.h_status, ws.status.p, 4 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, s));

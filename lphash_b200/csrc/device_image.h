@@ -33,6 +33,18 @@ struct DevEF {               // {high bit_vector, darray1, low compact_vector}
     uint64_t n;              // number of encoded values
 };
 
+// sizes_and_positions re-laid-out for one-sector lookups.  The reference stores the prefix sums
+// S[0]=0, S[i+1]=S[i]+d[i] in Elias-Fano form (include/ef_sequence.hpp) and reads S[i], S[i+1];
+// every d[i] is a super-k-mer size / minimizer offset (<= k-m+1 <= 63, src/partitioned_mphf.cpp:
+// 183-211), so 32 consecutive entries fit one 32-byte sector:
+//   word 0: S[32 s] in bits 0..47, sum of d[32 s .. 32 s + 15] in bits 48..63
+//   word 1: low nibbles of d[32 s + 0..15]      word 2: low nibbles of d[32 s + 16..31]
+//   word 3: top two bits of d[32 s + 0..31] (2 bits each)
+struct DevPrefix {
+    const uint64_t* sectors;  // null when some d[i] > 63 or S >= 2^48 (then DevEF is used instead)
+    uint64_t n;               // number of S entries
+};
+
 struct DevRank {             // rs_bit_vector re-laid-out: sector s = {ones before bit 192*s, 192 bits}
     const uint64_t* sectors; // 4 u64 per sector
     uint64_t nbits;
@@ -60,7 +72,8 @@ struct DevImage {
     uint64_t collision_base; // EF[none_pos_start] + w*n_maximal (global rank of colliding k-mers)
     DevPhf minimizer_order, fallback;
     DevRank root, left_right, max_none;
-    DevEF sp;                // sizes_and_positions
+    DevEF sp;                // sizes_and_positions (file layout; used when sp_fast.sectors == null)
+    DevPrefix sp_fast;       // same values, one 32-byte sector per 32 entries
 };
 
 }  // namespace lphb

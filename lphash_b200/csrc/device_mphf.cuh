@@ -126,6 +126,30 @@ LPHB_DEV void ef_pair(DevEF const& e, uint64_t i, uint64_t& v1, uint64_t& v2) {
     }
 }
 
+// S[i] and d = S[i+1] - S[i] from the prefix-sector layout (device_image.h: DevPrefix): one
+// 32-byte sector, SWAR sums of 4-bit / 2-bit fields.  Same values as ef_sequence::pair(i)
+// (ref: include/ef_sequence.hpp:83-94).
+LPHB_DEV void prefix_pair(DevPrefix const& t, uint64_t i, uint64_t& v1, uint32_t& d) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(t.sectors + 4 * (i >> 5));
+    const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+    const uint32_t j = uint32_t(i) & 31u, t16 = j & 15u;
+    const bool upper = j >= 16u;
+    const uint64_t nib = upper ? b.x : a.y;
+    const uint32_t top = upper ? uint32_t(b.y >> 32) : uint32_t(b.y);
+    d = (uint32_t(nib >> (4 * t16)) & 15u) | (((top >> (2 * t16)) & 3u) << 4);
+    // sum of the first t16 deltas of this half
+    const uint64_t nm = nib & ~(~uint64_t(0) << (4 * t16));
+    const uint32_t tm = top & ~(~0u << (2 * t16));
+    const uint32_t lo = uint32_t(nm), hi = uint32_t(nm >> 32);
+    uint32_t sn = (lo & 0x0F0F0F0Fu) + ((lo >> 4) & 0x0F0F0F0Fu) + (hi & 0x0F0F0F0Fu) + ((hi >> 4) & 0x0F0F0F0Fu);
+    sn = (sn * 0x01010101u) >> 24;  // <= 15 * 15
+    uint32_t sp = (tm & 0x33333333u) + ((tm >> 2) & 0x33333333u);
+    sp = (sp + (sp >> 4)) & 0x0F0F0F0Fu;
+    sp = (sp * 0x01010101u) >> 24;  // <= 15 * 3
+    const uint32_t half = upper ? uint32_t(a.x >> 48) : 0u;
+    v1 = (a.x & 0x0000FFFFFFFFFFFFull) + half + sn + 16u * sp;
+}
+
 // bit `pos` and rank of its own kind before it, one 32-byte sector.  Result equals
 // rs_bit_vector::operator[] + rank / rank0 (ref: include/rs_bit_vector.hpp:27-38, 101-114;
 // pos == nbits handled by the terminal sector).
@@ -162,6 +186,18 @@ LPHB_DEV void wtree_rank_of(DevImage const& f, uint64_t idx, uint32_t& type, uin
 // pthash::single_phf::position.  ref: pthash/include/single_phf.hpp:55-65;
 // skew_bucketer::bucket pthash/include/utils/bucketers.hpp:17-22 (T = (uint64_t)(0.6*UINT64_MAX)
 // evaluated in double = 0x9999999999999800); dual/dictionary access encoders.hpp:167-170,268-271.
+// position before the minimal remap (may be >= num_keys: then free_slots resolves it)
+LPHB_DEV uint64_t phf_raw_position(DevPhf const& p, uint64_t h) {
+    const uint64_t T = 0x9999999999999800ULL;
+    bool sm = p.small_divisors != 0;
+    uint64_t b = h < T ? mod_any(h, p.m_dense, p.dense, sm)
+                       : p.dense + mod_any(h, p.m_sparse, p.sparse, sm);
+    uint32_t rk = p.ranks_are_u16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(p.ranks) + b))
+                                  : __ldg(reinterpret_cast<const uint32_t*>(p.ranks) + b);
+    uint64_t hp = __ldg(p.hashed_pilots + rk);
+    return mod_any(h ^ hp, p.m_table, p.table_size, sm);
+}
+
 LPHB_DEV uint64_t phf_position(DevPhf const& p, uint64_t h) {
     const uint64_t T = 0x9999999999999800ULL;
     bool sm = p.small_divisors != 0;
@@ -198,12 +234,41 @@ struct Probe {
 //   COLL     v2 == v1: g = EF[none_pos_start] + w*n_max, l = fallback(kmer)
 //   MAXIMAL  g = w*rank,                              l = p
 //   NONE     g = EF[none_sizes_start+rank] + w*n_max, l = EF.diff(none_pos_start+rank) - p
-LPHB_DEV Probe probe_minimizer(DevImage const& f, uint64_t minimizer) {
+LPHB_DEV Probe probe_bucket(DevImage const& f, uint64_t bucket) {
     Probe out;
-    uint64_t bucket = phf_position(f.minimizer_order, murmur64(minimizer, f.minimizer_order.seed));
     uint32_t type;
     uint64_t rk;
     wtree_rank_of(f, bucket, type, rk);
+    if (f.sp_fast.sectors) {
+        // one prefix sector for every non-MAXIMAL type, a second one (offset only) for NONE
+        const uint64_t ia = type == T_LEFT ? rk : (type == T_RIGHT ? f.right_start + rk : f.none_sizes_start + rk);
+        uint64_t v1 = 0;
+        uint32_t d = 0, d2 = 0;
+        if (type != T_MAXIMAL) prefix_pair(f.sp_fast, ia, v1, d);
+        if (type == T_NONE) {
+            uint64_t unused;
+            prefix_pair(f.sp_fast, f.none_pos_start + rk, unused, d2);
+        }
+        if (type == T_MAXIMAL) {
+            out.base = uint64_t(f.w) * rk;
+            out.slope = 1;
+            out.type = T_MAXIMAL;
+        } else if (type == T_LEFT) {
+            out.base = v1 + f.maximal_block;
+            out.slope = 1;
+            out.type = T_LEFT;
+        } else if (type == T_RIGHT) {
+            const bool coll = d == 0;
+            out.base = coll ? f.collision_base : v1 + f.maximal_block + uint64_t(f.k - f.m);
+            out.slope = coll ? 0 : -1;
+            out.type = coll ? T_COLLISION : T_RIGHT;
+        } else {
+            out.base = v1 + f.maximal_block + d2;
+            out.slope = -1;
+            out.type = T_NONE;
+        }
+        return out;
+    }
     if (type == T_MAXIMAL) {
         out.base = uint64_t(f.w) * rk;
         out.slope = 1;
@@ -232,6 +297,10 @@ LPHB_DEV Probe probe_minimizer(DevImage const& f, uint64_t minimizer) {
         out.type = T_NONE;
     }
     return out;
+}
+
+LPHB_DEV Probe probe_minimizer(DevImage const& f, uint64_t minimizer) {
+    return probe_bucket(f, phf_position(f.minimizer_order, murmur64(minimizer, f.minimizer_order.seed)));
 }
 
 LPHB_DEV uint64_t probe_hval(Probe const& pr, uint32_t p) {

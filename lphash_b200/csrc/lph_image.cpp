@@ -96,7 +96,7 @@ void ImageBuilder::read_compact(Cursor& c, DevCompact& out) {
     out.bits = reinterpret_cast<const uint64_t*>(uintptr_t(off));
 }
 
-void ImageBuilder::read_ef(Cursor& c, DevEF& out) {
+void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast) {
     uint64_t nbits = c.pod<uint64_t>();
     uint64_t nw;
     const uint8_t* hw = c.vec<uint64_t>(nw);
@@ -117,9 +117,59 @@ void ImageBuilder::read_ef(Cursor& c, DevEF& out) {
     out.block_inv = append(reinterpret_cast<const int64_t*>(bi), nb, 1);
     out.sub_inv = append(reinterpret_cast<const uint16_t*>(si), ns, 4);
     out.overflow = append(reinterpret_cast<const uint64_t*>(ov), no, 1);
+    FileCompact low_view;
+    {
+        Cursor peek = c;  // the low-bits vector is parsed twice: once as a view, once into the arena
+        low_view = peek.compact();
+    }
     read_compact(c, out.low);
     out.n = out.low.size;
     if (out.n != positions) throw FormatError("EF: darray positions != number of values");
+    if (!fast) return;
+    // Decode every value once (value i = ((position of the i-th one) - i) << l | low[i],
+    // include/ef_sequence.hpp:77-81) and re-encode as prefix sectors (device_image.h).
+    fast->sectors = nullptr;
+    fast->n = out.n;
+    std::vector<uint64_t> vals;
+    vals.reserve(out.n);
+    for (uint64_t wi = 0; wi < nw && vals.size() < out.n; ++wi) {
+        uint64_t wv;
+        std::memcpy(&wv, hw + 8 * wi, 8);
+        while (wv && vals.size() < out.n) {
+            uint64_t pos = wi * 64 + uint64_t(__builtin_ctzll(wv));
+            wv &= wv - 1;
+            if (pos >= nbits) break;
+            uint64_t i = vals.size();
+            vals.push_back(((pos - i) << low_view.width) | low_view.get(i));
+        }
+    }
+    if (vals.size() != out.n) throw FormatError("EF: fewer set bits than values");
+    uint64_t nsec = out.n / 32 + 1;
+    std::vector<uint64_t> sec(nsec * 4, 0);
+    for (uint64_t s0 = 0; s0 < nsec; ++s0) {
+        uint64_t first = s0 * 32;
+        uint64_t base = first < out.n ? vals[first] : (out.n ? vals[out.n - 1] : 0);
+        if (base >> 48) return;  // does not fit: keep the EF path
+        uint64_t half = 0, nib[2] = {0, 0}, top = 0;
+        for (uint64_t j = 0; j < 32; ++j) {
+            uint64_t i = first + j;
+            uint64_t d = 0;
+            if (i + 1 < out.n) {
+                if (vals[i + 1] < vals[i]) throw FormatError("EF: values not monotone");
+                d = vals[i + 1] - vals[i];
+            }
+            if (d > 63) return;  // not a sizes/positions array after all: keep the EF path
+            if (j < 16) half += d;
+            nib[j >> 4] |= (d & 15) << (4 * (j & 15));
+            top |= (d >> 4) << (2 * j);
+        }
+        sec[4 * s0] = base | (half << 48);
+        sec[4 * s0 + 1] = nib[0];
+        sec[4 * s0 + 2] = nib[1];
+        sec[4 * s0 + 3] = top;
+    }
+    fast->sectors = append(sec.data(), sec.size(), 0);
+    fast_built_ = true;
 }
 
 void ImageBuilder::read_rank(Cursor& c, DevRank& out) {
@@ -246,7 +296,8 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     read_rank(c, img_.root);
     read_rank(c, img_.left_right);
     read_rank(c, img_.max_none);
-    read_ef(c, img_.sp);
+    fast_built_ = false;
+    read_ef(c, img_.sp, &img_.sp_fast);
     read_phf(c, img_.fallback);
     if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
     if (img_.minimizer_order.num_keys != img_.distinct_minimizers ||
@@ -286,6 +337,7 @@ DevImage ImageBuilder::rebased(const void* device_base) const {
     d.left_right.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.left_right.sectors));
     d.max_none.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.max_none.sectors));
     rebase_ef(d.sp, base);
+    if (fast_built_) d.sp_fast.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.sp_fast.sectors));
     return d;
 }
 

@@ -19,7 +19,10 @@ struct DevBatch {
     uint64_t* codes;            // output
     uint8_t* dirty;             // n_contigs flags: contig contains a non-ACGT byte
     unsigned long long* status; // [0] unused here, [1] += number of dirty contigs
+    void* tile_ws;              // scratch for the tiled kernel (query_tiled_ws_bytes), may be null
+    uint64_t tile_ws_bytes;
 };
+uint64_t query_tiled_ws_bytes(uint64_t span_bases);
 
 // code_off[c] = sum_{c' < c} max(0, L_c' - k + 1); status[0] = total.  One launch, any n.
 void launch_code_offsets(const uint64_t* d_offsets, uint64_t n_contigs, uint32_t k,
