@@ -96,6 +96,10 @@ struct lphb_mphf {
     int device = 0;
     DevImage img{};
     void* d_arena = nullptr;
+    uint64_t arena_bytes = 0;
+    uint64_t l2_window_bytes = 0;      // 0: persistence not available
+    cudaStream_t l2_stream = nullptr;  // last stream the window was attached to
+    bool l2_stream_set = false;
     lphb_info info{};
     lphb_stats stats{};
     bool events_pending = false;
@@ -149,6 +153,19 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
             CK(cudaMalloc(&f->d_arena, arena.size() + 256));
             CK(cudaMemcpy(f->d_arena, arena.data(), arena.size(), cudaMemcpyHostToDevice));
             f->img = builder.rebased(f->d_arena);
+            f->arena_bytes = arena.size();
+            {
+                int max_persist = 0, max_window = 0;
+                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+                cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+                uint64_t want = arena.size();
+                if (uint64_t(max_persist) < want) want = uint64_t(max_persist);
+                if (uint64_t(max_window) < want) want = uint64_t(max_window);
+                if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                    f->l2_window_bytes = want;
+                else
+                    cudaGetLastError();
+            }
             f->ws.init();
             // collision_base = EF[none_pos_start] + w*n_maximal, evaluated once by the device's
             // own EF code (src/partitioned_mphf.cpp:308-311)
@@ -183,7 +200,24 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
 }
 
 // main kernel bracketed by the handle's events (elapsed time is read lazily by lphb_mphf_stats)
+// Keep the image (a few bits per k-mer, gathered at random) resident in L2 while the base stream
+// and the codes (streamed once, marked evict-first in the kernels) flow through it.
+void attach_l2_window(lphb_mphf* f, cudaStream_t s) {
+    if (!f->l2_window_bytes || (f->l2_stream_set && f->l2_stream == s)) return;
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = f->d_arena;
+    attr.accessPolicyWindow.num_bytes = f->l2_window_bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+        cudaGetLastError();  // a hint only
+    f->l2_stream = s;
+    f->l2_stream_set = true;
+}
+
 void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
+    attach_l2_window(f, s);
     CK(cudaEventRecord(f->ws.ev0, s));
     if (!launch_query_tiled(f->img, b, s)) launch_query_generic(f->img, b, s);
     CK(cudaEventRecord(f->ws.ev1, s));

@@ -8,12 +8,13 @@
 //     (u16 when the two dictionaries together have <= 65536 entries, else u32) indexing ONE table
 //     that already holds default_hash64(pilot, seed) (single_phf.hpp:58): one 2-byte and one 8-byte
 //     load and no second murmur per probe.
-//   * rank bit-vectors (rs_bit_vector.hpp): bits and rank directory interleaved in 32-byte
-//     sectors {u64 ones_before, u64 bits[3]} so bit + rank cost one sector, not three.
+//   * rank bit-vectors (rs_bit_vector.hpp): bits and rank directory interleaved in 16-byte
+//     units {u32 ones_before, u32 bits[3]} so bit + rank cost one 16-byte load, not three lines.
 //   * Elias-Fano (include/ef_sequence.hpp, pthash ef_sequence.hpp): high bits, darray
 //     inventories and low bits kept as in the file, word-aligned and padded.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>  // uint4 (plain struct; usable from host-only translation units)
 
 namespace lphb {
 
@@ -45,9 +46,9 @@ struct DevPrefix {
     uint64_t n;               // number of S entries
 };
 
-struct DevRank {             // rs_bit_vector re-laid-out: sector s = {ones before bit 192*s, 192 bits}
-    const uint64_t* sectors; // 4 u64 per sector
-    uint64_t nbits;
+struct DevRank {             // rs_bit_vector re-laid-out: unit u = {ones before bit 96*u, 96 bits}
+    const uint4* units;      // x = ones before, y/z/w = bits 96u.., 96u+32.., 96u+64..
+    uint64_t nbits;          // < 2^32 (PTHash with 64-bit hashes holds <= 2^30 keys, hasher.hpp:27-31)
     uint64_t num_ones;
 };
 

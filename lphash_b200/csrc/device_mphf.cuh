@@ -150,35 +150,28 @@ LPHB_DEV void prefix_pair(DevPrefix const& t, uint64_t i, uint64_t& v1, uint32_t
     v1 = (a.x & 0x0000FFFFFFFFFFFFull) + half + sn + 16u * sp;
 }
 
-// bit `pos` and rank of its own kind before it, one 32-byte sector.  Result equals
-// rs_bit_vector::operator[] + rank / rank0 (ref: include/rs_bit_vector.hpp:27-38, 101-114;
-// pos == nbits handled by the terminal sector).
-LPHB_DEV void rank_sector(DevRank const& r, uint64_t pos, bool want_bit, uint32_t& bit,
-                          uint64_t& ones_before) {
-    uint64_t word = pos >> 6;
-    uint64_t sec = word / 3;
-    uint32_t wi = uint32_t(word - sec * 3);
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(r.sectors + 4 * sec);
-    ulonglong2 a = __ldg(p), b = __ldg(p + 1);
-    uint64_t w0 = a.y, w1 = b.x, w2 = b.y;
-    uint64_t cur = wi == 0 ? w0 : (wi == 1 ? w1 : w2);
-    uint64_t ones = a.x;
-    if (wi > 0) ones += uint64_t(__popcll(w0));
-    if (wi > 1) ones += uint64_t(__popcll(w1));
-    uint32_t sh = uint32_t(pos & 63);
-    ones += uint64_t(__popcll(cur & ((uint64_t(1) << sh) - 1)));
+// bit `pos` and the number of ones before it: one 16-byte unit {ones before, 96 bits}.  Equals
+// rs_bit_vector::operator[] and rank (ref: include/rs_bit_vector.hpp:27-38, 101-114; pos == nbits
+// is served by the terminal unit).
+LPHB_DEV void rank_unit(DevRank const& r, uint32_t pos, uint32_t& bit, uint32_t& ones_before) {
+    const uint32_t u = __umulhi(pos, 0xAAAAAAABu) >> 6;  // pos / 96
+    const uint32_t off = pos - u * 96u;
+    const uint4 v = __ldg(r.units + u);
+    const uint32_t wi = off >> 5, sh = off & 31u;
+    const uint32_t cur = wi == 0 ? v.y : (wi == 1 ? v.z : v.w);
+    uint32_t ones = v.x + __popc(cur & ((1u << sh) - 1u));
+    if (wi > 0) ones += __popc(v.y);
+    if (wi > 1) ones += __popc(v.z);
     ones_before = ones;
-    bit = want_bit ? uint32_t((cur >> sh) & 1) : 0u;
+    bit = (cur >> sh) & 1u;
 }
 
 // quartet_wtree::rank_of.  ref: src/quartet_wtree.cpp:84-99.
 LPHB_DEV void wtree_rank_of(DevImage const& f, uint64_t idx, uint32_t& type, uint64_t& rank) {
-    uint32_t msb, lsb;
-    uint64_t ones;
-    rank_sector(f.root, idx, true, msb, ones);
-    uint64_t r = msb ? ones : idx - ones;
-    DevRank const& leaf = msb ? f.max_none : f.left_right;
-    rank_sector(leaf, r, true, lsb, ones);
+    uint32_t msb, lsb, ones;
+    rank_unit(f.root, uint32_t(idx), msb, ones);
+    const uint32_t r = msb ? ones : uint32_t(idx) - ones;
+    rank_unit(msb ? f.max_none : f.left_right, r, lsb, ones);
     rank = lsb ? ones : r - ones;
     type = (msb << 1) | lsb;
 }

@@ -189,20 +189,22 @@ void ImageBuilder::read_rank(Cursor& c, DevRank& out) {
         }
         return v;
     };
-    // sector s covers bits [192 s, 192 s + 192); one extra sector so that rank(nbits) needs no
-    // special case (rs_bit_vector.hpp:27-29 returns num_ones there)
-    uint64_t nsec = nbits / 192 + 2;
-    std::vector<uint64_t> sec(nsec * 4, 0);
+    // unit u covers bits [96 u, 96 u + 96); one extra unit so that rank(nbits) needs no special
+    // case (rs_bit_vector.hpp:27-29 returns num_ones there)
+    if (nbits >> 32) throw FormatError("rank bit vector longer than 2^32 bits");
+    auto word32 = [&](uint64_t i) -> uint32_t { return uint32_t(word(i >> 1) >> (32 * (i & 1))); };
+    uint64_t nunits = nbits / 96 + 2;
+    std::vector<uint32_t> units(nunits * 4, 0);
     uint64_t ones = 0;
-    for (uint64_t s = 0; s < nsec; ++s) {
-        sec[4 * s] = ones;
+    for (uint64_t u = 0; u < nunits; ++u) {
+        units[4 * u] = uint32_t(ones);
         for (int j = 0; j < 3; ++j) {
-            uint64_t v = word(3 * s + j);
-            sec[4 * s + 1 + j] = v;
-            ones += uint64_t(__builtin_popcountll(v));
+            uint32_t v = word32(3 * u + j);
+            units[4 * u + 1 + j] = v;
+            ones += uint64_t(__builtin_popcount(v));
         }
     }
-    out.sectors = append(sec.data(), sec.size(), 0);
+    out.units = reinterpret_cast<const uint4*>(append(units.data(), units.size(), 0));
     out.nbits = nbits;
     out.num_ones = ones;
 }
@@ -333,9 +335,9 @@ DevImage ImageBuilder::rebased(const void* device_base) const {
     auto* base = static_cast<const uint8_t*>(device_base);
     rebase_phf(d.minimizer_order, base);
     rebase_phf(d.fallback, base);
-    d.root.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.root.sectors));
-    d.left_right.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.left_right.sectors));
-    d.max_none.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.max_none.sectors));
+    d.root.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.root.units));
+    d.left_right.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.left_right.units));
+    d.max_none.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.max_none.units));
     rebase_ef(d.sp, base);
     if (fast_built_) d.sp_fast.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.sp_fast.sectors));
     return d;

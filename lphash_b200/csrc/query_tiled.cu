@@ -81,7 +81,7 @@ struct Cfg {
 };
 
 template <int K, int M>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
@@ -346,22 +346,35 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     // position-parallel, coalesced 8-byte stores straight to the output.
     uint64_t* out = b.codes + a.tile_out[tile];
     const bool all_valid = s_n_invalid == 0;
-#pragma unroll 2
-    for (int q = tid; q < kTile; q += kThreads) {
-        const uint32_t p = s_pos[q];
-        const int bp = q + int(p);
-        const int32_t st = s_step[bp];
-        const uint64_t code = s_base[bp] + uint64_t(int64_t(st * int32_t(p)));
-        int oidx = q;
-        bool valid = true;
-        if (!all_valid) {
-            uint32_t mw = s_invalid[q >> 5];
-            valid = !((mw >> (q & 31)) & 1u);
-            oidx = q - int(s_invpre[q >> 5] + __popc(mw & ((1u << (q & 31)) - 1u)));
+    if (all_valid) {
+        // 15.5 rounds of 256 consecutive k-mers: fully unrolled, 32-bit shared-memory indexing
+        uint64_t* o = out + tid;
+        constexpr int kRounds = (kTile + kThreads - 1) / kThreads;
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int q = tid + r * kThreads;
+            if (r * kThreads + kThreads <= kTile || q < kTile) {
+                const uint32_t p = s_pos[q];
+                const int bp = q + int(p);
+                const int32_t st = s_step[bp];
+                const int32_t sp = st > 0 ? int32_t(p) : -int32_t(p);
+                const uint64_t code = s_base[bp] + uint64_t(int64_t(sp));
+                if (st != 0) __stcs(o + r * kThreads, code);
+                else s_list[atomicAdd(&s_n_fb, 1u)] = uint16_t(q);  // colliding minimizer: needs the k-mer
+            }
         }
-        if (valid) {
+    } else {
+        for (int q = tid; q < kTile; q += kThreads) {
+            const uint32_t mw = s_invalid[q >> 5];
+            if ((mw >> (q & 31)) & 1u) continue;
+            const uint32_t p = s_pos[q];
+            const int bp = q + int(p);
+            const int32_t st = s_step[bp];
+            const int32_t sp = st > 0 ? int32_t(p) : -int32_t(p);
+            const uint64_t code = s_base[bp] + uint64_t(int64_t(sp));
+            const int oidx = q - int(s_invpre[q >> 5] + __popc(mw & ((1u << (q & 31)) - 1u)));
             if (st != 0) __stcs(out + oidx, code);
-            else s_list[atomicAdd(&s_n_fb, 1u)] = uint16_t(q);  // colliding minimizer: needs the k-mer
+            else s_list[atomicAdd(&s_n_fb, 1u)] = uint16_t(q);
         }
     }
     __syncthreads();
