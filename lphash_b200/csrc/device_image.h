@@ -61,7 +61,9 @@ struct DevPhf {              // pthash::single_phf<*, dictionary_dictionary, tru
     uint32_t ranks_are_u16;
     const void* ranks;       // one entry per bucket, index into hashed_pilots
     const uint64_t* hashed_pilots;
-    DevEF free_slots;
+    DevEF free_slots;        // file layout (pthash ef_sequence<false>)
+    const uint32_t* free32;  // the same values decoded (null if one does not fit 32 bits):
+                             // free32[i] == free_slots.access(i), single_phf.hpp:61-63
 };
 
 struct DevImage {

@@ -47,8 +47,13 @@ LPHB_DEV uint32_t mod_small(uint64_t a, const uint32_t M[3], uint32_t d) {
     return uint32_t(q);
 }
 
+// rarely-taken paths are kept out of line so that the hot loops stay small in the instruction cache
+#define LPHB_COLD static __device__ __noinline__
+
+LPHB_COLD uint64_t mod_slow(uint64_t a, uint64_t d) { return a % d; }
+
 LPHB_DEV uint64_t mod_any(uint64_t a, const uint32_t M[3], uint64_t d, bool small) {
-    return small ? uint64_t(mod_small(a, M, uint32_t(d))) : a % d;
+    return small ? uint64_t(mod_small(a, M, uint32_t(d))) : mod_slow(a, d);
 }
 
 // compact_vector::access.  ref: pthash/include/encoders/compact_vector.hpp:229-234 (an unaligned
@@ -83,7 +88,7 @@ LPHB_DEV uint32_t select_in_word(uint64_t x, uint32_t r) {
 }
 
 // darray1::select.  ref: pthash/include/encoders/darray.hpp:51-76 (block 1024, subblock 32).
-LPHB_DEV uint64_t darray_select(DevEF const& e, uint64_t idx) {
+LPHB_COLD uint64_t darray_select(DevEF const& e, uint64_t idx) {
     int64_t bp = __ldg(e.block_inv + (idx >> 10));
     if (bp < 0) return __ldg(e.overflow + uint64_t(-bp - 1) + (idx & 1023));
     uint64_t start = uint64_t(bp) + __ldg(e.sub_inv + (idx >> 5));
@@ -192,16 +197,10 @@ LPHB_DEV uint64_t phf_raw_position(DevPhf const& p, uint64_t h) {
 }
 
 LPHB_DEV uint64_t phf_position(DevPhf const& p, uint64_t h) {
-    const uint64_t T = 0x9999999999999800ULL;
-    bool sm = p.small_divisors != 0;
-    uint64_t b = h < T ? mod_any(h, p.m_dense, p.dense, sm)
-                       : p.dense + mod_any(h, p.m_sparse, p.sparse, sm);
-    uint32_t rk = p.ranks_are_u16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(p.ranks) + b))
-                                  : __ldg(reinterpret_cast<const uint32_t*>(p.ranks) + b);
-    uint64_t hp = __ldg(p.hashed_pilots + rk);
-    uint64_t pos = mod_any(h ^ hp, p.m_table, p.table_size, sm);
+    uint64_t pos = phf_raw_position(p, h);
     if (pos < p.num_keys) return pos;
-    return ef_access(p.free_slots, pos - p.num_keys);
+    if (p.free32) return __ldg(p.free32 + (pos - p.num_keys));
+    return ef_access(p.free_slots, pos - p.num_keys);  // cold: darray_select is out of line
 }
 
 // fallback_kmer_order(kmer).  ref: include/constants.hpp:56-70 (fallback_hasher: 64-bit kmer_t
@@ -227,6 +226,39 @@ struct Probe {
 //   COLL     v2 == v1: g = EF[none_pos_start] + w*n_max, l = fallback(kmer)
 //   MAXIMAL  g = w*rank,                              l = p
 //   NONE     g = EF[none_sizes_start+rank] + w*n_max, l = EF.diff(none_pos_start+rank) - p
+// file-layout Elias-Fano path (only when the prefix sectors could not be built)
+LPHB_COLD Probe probe_bucket_ef(DevImage const& f, uint32_t type, uint64_t rk) {
+    Probe out;
+    if (type == T_MAXIMAL) {
+        out.base = uint64_t(f.w) * rk;
+        out.slope = 1;
+        out.type = T_MAXIMAL;
+    } else if (type == T_LEFT) {
+        out.base = ef_access(f.sp, rk) + f.maximal_block;
+        out.slope = 1;
+        out.type = T_LEFT;
+    } else if (type == T_RIGHT) {
+        uint64_t v1, v2;
+        ef_pair(f.sp, f.right_start + rk, v1, v2);
+        if (v2 == v1) {
+            out.base = f.collision_base;
+            out.slope = 0;
+            out.type = T_COLLISION;
+        } else {
+            out.base = v1 + f.maximal_block + uint64_t(f.k - f.m);
+            out.slope = -1;
+            out.type = T_RIGHT;
+        }
+    } else {
+        uint64_t v1, v2;
+        ef_pair(f.sp, f.none_pos_start + rk, v1, v2);
+        out.base = ef_access(f.sp, f.none_sizes_start + rk) + f.maximal_block + (v2 - v1);
+        out.slope = -1;
+        out.type = T_NONE;
+    }
+    return out;
+}
+
 LPHB_DEV Probe probe_bucket(DevImage const& f, uint64_t bucket) {
     Probe out;
     uint32_t type;
@@ -262,34 +294,7 @@ LPHB_DEV Probe probe_bucket(DevImage const& f, uint64_t bucket) {
         }
         return out;
     }
-    if (type == T_MAXIMAL) {
-        out.base = uint64_t(f.w) * rk;
-        out.slope = 1;
-        out.type = T_MAXIMAL;
-    } else if (type == T_LEFT) {
-        out.base = ef_access(f.sp, rk) + f.maximal_block;
-        out.slope = 1;
-        out.type = T_LEFT;
-    } else if (type == T_RIGHT) {
-        uint64_t v1, v2;
-        ef_pair(f.sp, f.right_start + rk, v1, v2);
-        if (v2 == v1) {
-            out.base = f.collision_base;
-            out.slope = 0;
-            out.type = T_COLLISION;
-        } else {
-            out.base = v1 + f.maximal_block + uint64_t(f.k - f.m);
-            out.slope = -1;
-            out.type = T_RIGHT;
-        }
-    } else {
-        uint64_t v1, v2;
-        ef_pair(f.sp, f.none_pos_start + rk, v1, v2);
-        out.base = ef_access(f.sp, f.none_sizes_start + rk) + f.maximal_block + (v2 - v1);
-        out.slope = -1;
-        out.type = T_NONE;
-    }
-    return out;
+    return probe_bucket_ef(f, type, rk);
 }
 
 LPHB_DEV Probe probe_minimizer(DevImage const& f, uint64_t minimizer) {

@@ -96,7 +96,7 @@ void ImageBuilder::read_compact(Cursor& c, DevCompact& out) {
     out.bits = reinterpret_cast<const uint64_t*>(uintptr_t(off));
 }
 
-void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast) {
+void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast, std::vector<uint64_t>* decoded) {
     uint64_t nbits = c.pod<uint64_t>();
     uint64_t nw;
     const uint8_t* hw = c.vec<uint64_t>(nw);
@@ -125,11 +125,13 @@ void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast) {
     read_compact(c, out.low);
     out.n = out.low.size;
     if (out.n != positions) throw FormatError("EF: darray positions != number of values");
-    if (!fast) return;
+    if (!fast && !decoded) return;
     // Decode every value once (value i = ((position of the i-th one) - i) << l | low[i],
     // include/ef_sequence.hpp:77-81) and re-encode as prefix sectors (device_image.h).
-    fast->sectors = nullptr;
-    fast->n = out.n;
+    if (fast) {
+        fast->sectors = nullptr;
+        fast->n = out.n;
+    }
     std::vector<uint64_t> vals;
     vals.reserve(out.n);
     for (uint64_t wi = 0; wi < nw && vals.size() < out.n; ++wi) {
@@ -144,6 +146,8 @@ void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast) {
         }
     }
     if (vals.size() != out.n) throw FormatError("EF: fewer set bits than values");
+    if (decoded) *decoded = vals;
+    if (!fast) return;
     uint64_t nsec = out.n / 32 + 1;
     std::vector<uint64_t> sec(nsec * 4, 0);
     for (uint64_t s0 = 0; s0 < nsec; ++s0) {
@@ -270,14 +274,25 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
         if (out.dense) reciprocal96(out.dense, out.m_dense);
         if (out.sparse) reciprocal96(out.sparse, out.m_sparse);
     }
-    read_ef(c, out.free_slots);
+    std::vector<uint64_t> free_vals;
+    read_ef(c, out.free_slots, nullptr, &free_vals);
     if (out.free_slots.n != out.table_size - out.num_keys)
         throw FormatError("single_phf: free-slot count mismatch");
+    // minimal remap as a plain array: one load instead of an Elias-Fano select
+    out.free32 = nullptr;
+    bool fits = true;
+    for (uint64_t v : free_vals) fits = fits && v < (1ull << 32);
+    if (fits) {
+        std::vector<uint32_t> f32(free_vals.begin(), free_vals.end());
+        out.free32 = append(f32.data(), f32.size(), 4);
+        has_free32_.push_back(&out == &img_.minimizer_order ? 0 : 1);
+    }
 }
 
 void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (kmer_bits != 64 && kmer_bits != 128) throw FormatError("kmer_bits must be 64 or 128");
     arena_.clear();
+    has_free32_.clear();
     img_ = DevImage{};
     Cursor c{data, data + n};
     img_.k = c.pod<uint8_t>();
@@ -324,7 +339,8 @@ void ImageBuilder::rebase_ef(DevEF& e, const uint8_t* base) {
     e.overflow = reinterpret_cast<const uint64_t*>(base + uintptr_t(e.overflow));
     rebase_compact(e.low, base);
 }
-void ImageBuilder::rebase_phf(DevPhf& p, const uint8_t* base) {
+void ImageBuilder::rebase_phf(DevPhf& p, const uint8_t* base, bool has_free32) {
+    if (has_free32) p.free32 = reinterpret_cast<const uint32_t*>(base + uintptr_t(p.free32));
     p.ranks = base + uintptr_t(p.ranks);
     p.hashed_pilots = reinterpret_cast<const uint64_t*>(base + uintptr_t(p.hashed_pilots));
     rebase_ef(p.free_slots, base);
@@ -333,8 +349,10 @@ void ImageBuilder::rebase_phf(DevPhf& p, const uint8_t* base) {
 DevImage ImageBuilder::rebased(const void* device_base) const {
     DevImage d = img_;
     auto* base = static_cast<const uint8_t*>(device_base);
-    rebase_phf(d.minimizer_order, base);
-    rebase_phf(d.fallback, base);
+    bool f0 = false, f1 = false;
+    for (int w : has_free32_) (w == 0 ? f0 : f1) = true;
+    rebase_phf(d.minimizer_order, base, f0);
+    rebase_phf(d.fallback, base, f1);
     d.root.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.root.units));
     d.left_right.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.left_right.units));
     d.max_none.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.max_none.units));

@@ -40,17 +40,19 @@ private:
     template <class T>
     const T* append(const T* src, uint64_t n, uint64_t pad_elems = 0);
     void read_compact(Cursor& c, DevCompact& out);
-    void read_ef(Cursor& c, DevEF& out, DevPrefix* fast = nullptr);
+    // decoded (optional): receives every value of the sequence
+    void read_ef(Cursor& c, DevEF& out, DevPrefix* fast = nullptr, std::vector<uint64_t>* decoded = nullptr);
     void read_rank(Cursor& c, DevRank& out);
     void read_phf(Cursor& c, DevPhf& out);
     static void rebase_compact(DevCompact& c, const uint8_t* base);
     static void rebase_ef(DevEF& e, const uint8_t* base);
-    static void rebase_phf(DevPhf& p, const uint8_t* base);
+    static void rebase_phf(DevPhf& p, const uint8_t* base, bool has_free32);
 
     std::vector<uint8_t> arena_;
     DevImage img_{};
     uint64_t fallback_keys_ = 0, file_bytes_ = 0;
     bool fast_built_ = false;
+    std::vector<int> has_free32_;  // 0: minimizer_order, 1: fallback
 };
 
 // ceil(2^96 / d) as three 32-bit limbs (d >= 1, d < 2^32); limbs all zero for d == 1.

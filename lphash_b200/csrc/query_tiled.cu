@@ -35,16 +35,23 @@ namespace lphb {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kS = 16;                        // k-mer starts per thread = bases per packed word
-constexpr int kLanes = 31;                    // producing lanes per warp
-constexpr int kTile = kWarps * kLanes * kS;   // 3968 k-mer starts per tile
-constexpr int kMaskWords = kTile / 32;        // 124
-constexpr int kPosSlots = kTile + 32;         // positions a minimizer can sit at: kTile + W - 1, rounded
-constexpr int kMaskSlots = kPosSlots / 32;    // 125
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kS = 16;                         // k-mer starts per thread = bases per packed word
+constexpr int kLanes = 31;                     // producing lanes per warp (lane 31 only feeds lane 30)
+constexpr int kStrip = kLanes * kS;            // 496 k-mer starts per warp pass
+constexpr int kStrips = 2;                     // passes per warp
+constexpr int kWarpKmers = kStrips * kStrip;   // 992 k-mer starts per warp
+constexpr int kTile = kWarps * kWarpKmers;     // 3968 k-mer starts per tile (CTA)
+constexpr int kMaskWords = kTile / 32;         // 124
+constexpr int kMaskSlots = kMaskWords + 1;
+constexpr int kWarpSlots = kWarpKmers + 32;    // positions a minimizer of the warp's k-mers can sit at
+constexpr int kWarpMaskWords = kWarpSlots / 32;  // 32: one word per lane
+constexpr int kCap = 256;                      // probe results held at once per warp
+constexpr int kWarpBytes = kWarpSlots * (1 + 2 + 2) + kCap * 8 + (kWarpMaskWords + 4) * 4;
 constexpr int kPackedSlots = 256;
-constexpr int kSmemBytes = kPosSlots * (8 + 1 + 1 + 2 + 2) + kPackedSlots * 4 + kMaskSlots * (4 + 4 + 2) + 16;
+constexpr int kSmemBytes = kWarps * kWarpBytes + kPackedSlots * 4 + kMaskSlots * (4 + 2) + 16;
+static_assert(kWarpMaskWords == 32 && kWarpBytes % 16 == 0, "per-warp layout");
 
 struct TileArgs {
     const char* abase;          // 16-byte aligned; stream position pos0 lives here
@@ -69,6 +76,29 @@ __device__ __forceinline__ uint32_t bad4(uint32_t x, uint32_t y) {
     return (u ^ c1) & (u ^ c2);
 }
 
+// flag the contig of every in-range non-ACGT byte of a 16-byte word (rare; out of line)
+static __device__ __noinline__ void mark_dirty(DevBatch const& b, uint4 v, int64_t wpos) {
+    const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
+    uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < 16; ++j) {
+        int64_t p = wpos + j;
+        uint32_t ch = (xs[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        if (p >= first && p < end && nt4(ch) > 3) {
+            uint64_t lo = 0, hi = b.n_contigs;
+            while (hi - lo > 1) {
+                uint64_t mid = (lo + hi) >> 1;
+                if (int64_t(__ldg(b.offsets + mid)) <= p) lo = mid; else hi = mid;
+            }
+            b.dirty[lo] = 1;
+        }
+    }
+}
+
+// code of a k-mer whose minimizer collides: fallback_kmer_order (rare; out of line)
+static __device__ __noinline__ uint64_t fallback_code(DevImage const& f, uint64_t klo, uint64_t khi) {
+    return f.collision_base + fallback_order(f, klo, khi);
+}
+
 template <int K, int M>
 struct Cfg {
     static constexpr int W = K - M + 1;
@@ -77,67 +107,86 @@ struct Cfg {
     static constexpr int TileWords = kTile / 16 + NW;        // words staged per tile
     static_assert(W >= 1 && W <= 17, "tiled kernel: window must fit one shuffle hop");
     static_assert(M <= 31 && K <= 63, "k, m out of range");
-    static_assert(TileWords <= kThreads, "one load per thread");
+    static_assert(TileWords <= kPackedSlots, "packed tile must fit its shared-memory array");
 };
 
+// Codes of the k-mers [q0, q1) of a warp whose minimizers are list entries [i0, i1) (their probe
+// results sit in s_base[0 .. i1-i0)).  `checked` = some starts of the tile produce no code.
+template <bool kChecked, bool kChunked>
+__device__ __forceinline__ void emit_codes(int lane, int wbase, uint32_t i0, uint32_t i1,
+                                           const uint8_t* s_pos, const uint16_t* s_ref,
+                                           const uint64_t* s_base, uint16_t* s_list,
+                                           uint32_t* s_n_fb, const uint32_t* s_invalid,
+                                           const uint16_t* s_invpre, uint64_t* out) {
+    uint64_t* o = out + wbase + lane;
+#pragma unroll 4
+    for (int r = 0; r < kWarpKmers / 32; ++r) {
+        const int q = lane + r * 32;
+        const uint32_t p = s_pos[q];
+        const uint32_t ref = s_ref[q + int(p)];
+        const uint32_t idx = ref & 0x3FFFu, kind = ref >> 14;  // kind 1: +p, 2: -p, 0: collision
+        if (kChunked && (idx < i0 || idx >= i1)) continue;
+        const int32_t sp = kind == 1 ? int32_t(p) : -int32_t(p);
+        const uint64_t code = s_base[idx - i0] + uint64_t(int64_t(sp));
+        if (!kChecked) {
+            if (kind != 0) __stcs(o + r * 32, code);
+            else s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);  // colliding minimizer: needs the k-mer
+        } else {
+            const int g = wbase + q;
+            const uint32_t mw = s_invalid[g >> 5];
+            if ((mw >> (g & 31)) & 1u) continue;
+            const int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
+            if (kind != 0) __stcs(out + oidx, code);
+            else s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);
+        }
+    }
+}
+
 template <int K, int M>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 6)
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
     constexpr int W = C::W, NW = C::NW, NH = C::NH;
     static_assert(NH <= 32, "per-thread minimizer marks must fit one 32-bit mask");
 
-    // dynamic shared memory, carved by hand (~58 KB: above the 48 KB static limit)
+    // dynamic shared memory: one private region per warp (warp-local coordinates) + tile-wide
+    // packed bases and invalid-start bitmask
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* s_base = reinterpret_cast<uint64_t*>(smem_raw);               // per minimizer position: probe result
-    int8_t* s_step = reinterpret_cast<int8_t*>(s_base + kPosSlots);         // per minimizer position: +1 / -1 / 0 (collision)
-    uint8_t* s_pos = reinterpret_cast<uint8_t*>(s_step + kPosSlots);        // per k-mer: minimizer offset p
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_pos + kPosSlots);      // minimizer positions to probe; later: colliding k-mers
-    uint16_t* s_retry = s_list + kPosSlots;                                 // probes that need the free-slot remap
-    uint32_t* s_packed = reinterpret_cast<uint32_t*>(s_retry + kPosSlots);  // 2-bit bases
-    uint32_t* s_minmask = s_packed + kPackedSlots;     // bit b: position b is some k-mer's minimizer
-    uint32_t* s_invalid = s_minmask + kMaskSlots;      // bit q: k-mer start q produces no code
-    uint16_t* s_invpre = reinterpret_cast<uint16_t*>(s_invalid + kMaskSlots);  // invalid starts before word
-    __shared__ uint32_t s_warp_cnt[kWarps];
-    __shared__ uint32_t s_n_min, s_n_retry, s_n_fb, s_n_invalid;
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* mine = smem_raw + warp * kWarpBytes;
+    uint64_t* s_base = reinterpret_cast<uint64_t*>(mine);                  // per probe (list index): result
+    uint8_t* s_pos = reinterpret_cast<uint8_t*>(s_base + kCap);            // per k-mer: minimizer offset p
+    uint16_t* s_ref = reinterpret_cast<uint16_t*>(s_pos + kWarpSlots);     // per position: list index | kind << 14
+    uint16_t* s_list = s_ref + kWarpSlots;                                 // minimizer positions (chunk); later colliding k-mers (<= kWarpKmers)
+    uint32_t* s_minmask = reinterpret_cast<uint32_t*>(s_list + kWarpSlots);  // bit b: position b is some k-mer's minimizer
+    uint32_t* s_n_fb = s_minmask + kWarpMaskWords;                         // colliding k-mers queued
+    uint32_t* s_packed = reinterpret_cast<uint32_t*>(smem_raw + kWarps * kWarpBytes);  // 2-bit bases (tile)
+    uint32_t* s_invalid = s_packed + kPackedSlots;     // bit q: k-mer start q produces no code (tile)
+    uint16_t* s_invpre = reinterpret_cast<uint16_t*>(s_invalid + kMaskSlots);  // invalid starts before word
+    __shared__ uint32_t s_n_invalid;
+
     const uint32_t tile = blockIdx.x;
     const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
     const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
 
     // ---------------------------------------------------------------- A: load + pack ------------
-    if (tid < kMaskSlots) { s_invalid[tid] = 0; s_minmask[tid] = 0; }
-    if (tid == 0) { s_n_retry = 0; s_n_fb = 0; s_n_invalid = 0; }
-    if (tid >= C::TileWords) s_packed[tid] = 0;
-    if (tid < C::TileWords) {
-        int64_t wpos = T0 + int64_t(tid) * 16;
+    if (tid < kMaskSlots) s_invalid[tid] = 0;
+    s_minmask[lane] = 0;
+    if (lane == 0) *s_n_fb = 0;
+    for (int t = tid; t < kPackedSlots; t += kThreads) {
+        int64_t wpos = T0 + int64_t(t) * 16;
         uint32_t word = 0;
-        if (wpos + 16 > first && wpos < end) {
+        if (t < C::TileWords && wpos + 16 > first && wpos < end) {
             const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.abase + (wpos - a.pos0)));
             uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
             word = (pack4(y0) << 24) | (pack4(y1) << 16) | (pack4(y2) << 8) | pack4(y3);
             uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
-            if (bad) {  // rare: flag the contig of every in-range invalid byte
-                uint32_t xs[4] = {v.x, v.y, v.z, v.w};
-                for (int j = 0; j < 16; ++j) {
-                    int64_t p = wpos + j;
-                    uint32_t ch = (xs[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    if (p >= first && p < end && nt4(ch) > 3) {
-                        uint64_t lo = 0, hi = b.n_contigs;
-                        while (hi - lo > 1) {
-                            uint64_t mid = (lo + hi) >> 1;
-                            if (int64_t(__ldg(b.offsets + mid)) <= p) lo = mid; else hi = mid;
-                        }
-                        b.dirty[lo] = 1;
-                    }
-                }
-            }
+            if (bad) mark_dirty(b, v, wpos);  // rare
         }
-        s_packed[tid] = word;
+        s_packed[t] = word;
     }
-    __syncthreads();
+    __syncthreads();  // zeroed masks + packed words visible
 
     // warp 0: rasterise the k-mer starts that produce no code (contig seams, short contigs,
     // positions outside [first, end)) into s_invalid
@@ -203,13 +252,16 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         }
         if (lane == 31) s_n_invalid = inc;
     }
+    __syncthreads();  // invalid-start mask ready; from here on every warp runs on its own
 
     // ---------------------------------------------------------------- B: per-thread scan --------
-    const int seg = (warp * kLanes + lane) * kS;  // tile-local position of this thread's first k-mer
-    {
+    const int wbase = warp * kWarpKmers;  // tile-local position of this warp's first k-mer
+#pragma unroll 1
+    for (int strip = 0; strip < kStrips; ++strip) {
+        const int lseg = strip * kStrip + lane * kS;  // warp-local position of this thread's first k-mer
         uint32_t wds[NW];
 #pragma unroll
-        for (int j = 0; j < NW; ++j) wds[j] = s_packed[(seg >> 4) + j];
+        for (int j = 0; j < NW; ++j) wds[j] = s_packed[((wbase + lseg) >> 4) + j];
 
         uint64_t h[NH];
 #pragma unroll
@@ -269,147 +321,101 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             pk[i >> 2] |= (bpos - i) << (8 * (i & 3));
         }
         if (lane < kLanes) {  // lane 31 only feeds hashes to lane 30
-            *reinterpret_cast<uint4*>(s_pos + seg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            // seg is a multiple of 16: the 32 local positions straddle at most two mask words
-            const int sh = seg & 16;
-            atomicOr(&s_minmask[seg >> 5], marks << sh);
-            if (sh && (marks >> 16)) atomicOr(&s_minmask[(seg >> 5) + 1], marks >> 16);
+            *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            // lseg is a multiple of 16: the 32 local positions straddle at most two mask words
+            const int sh = lseg & 16;
+            atomicOr(&s_minmask[lseg >> 5], marks << sh);
+            if (sh && (marks >> 16)) atomicOr(&s_minmask[(lseg >> 5) + 1], marks >> 16);
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---------------------------------------------------------------- C: list of minimizers -----
-    {
-        uint32_t word = tid < kMaskSlots ? s_minmask[tid] : 0u;
-        uint32_t n_mine = __popc(word);
-        uint32_t inc = n_mine;
+    // ---------------------------------------------------------------- C: rank the minimizers ----
+    // lane l owns mask word l: list index of every marked position -> s_ref
+    uint32_t my_word = s_minmask[lane];
+    uint32_t n_mine = __popc(my_word);
+    uint32_t inc = n_mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_warp_cnt[warp] = inc;
-        __syncthreads();
-        uint32_t warp_base = 0, total = 0;
-#pragma unroll
-        for (int wi = 0; wi < kWarps; ++wi) {
-            uint32_t v = s_warp_cnt[wi];
-            if (wi < warp) warp_base += v;
-            total += v;
-        }
-        uint32_t o = warp_base + inc - n_mine;
-        while (word) {
-            int bit = __ffs(word) - 1;
-            word &= word - 1;
-            s_list[o++] = uint16_t(tid * 32 + bit);
-        }
-        if (tid == 0) s_n_min = total;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += v;
     }
-    __syncthreads();
+    const uint32_t n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    const uint32_t my_first = inc - n_mine;
 
-    // ---------------------------------------------------------------- D: probe ------------------
-    // One thread per distinct minimizer position: m-mer -> PTHash bucket (probes that land in the
-    // free-slot region are queued and remapped densely afterwards, single_phf.hpp:61-63) ->
-    // wavelet tree -> sizes_and_positions.  Result indexed by minimizer position.
-    const uint32_t n_min = s_n_min;
-    for (uint32_t idx = tid; idx < n_min; idx += kThreads) {
-        const int bp = s_list[idx];
-        const int wi = bp >> 4, r = (bp & 15) * 2;
-        uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1], w2 = s_packed[wi + 2];
-        uint32_t hi = __funnelshift_l(w1, w0, r), lo = __funnelshift_l(w2, w1, r);
-        uint64_t mm = ((uint64_t(hi) << 32) | lo) >> (64 - 2 * M);
-        uint64_t pos = phf_raw_position(f.minimizer_order, murmur64(mm, f.minimizer_order.seed));
-        if (pos < f.minimizer_order.num_keys) {
-            Probe pr = probe_bucket(f, pos);
-            s_base[bp] = pr.base;
-            s_step[bp] = int8_t(pr.slope);
-        } else {
-            s_base[bp] = pos;
-            s_retry[atomicAdd(&s_n_retry, 1u)] = uint16_t(bp);
-        }
-    }
-    __syncthreads();
-    {
-        const uint32_t n_retry = s_n_retry;
-        for (uint32_t idx = tid; idx < n_retry; idx += kThreads) {
-            const int bp = s_retry[idx];
-            uint64_t pos = ef_access(f.minimizer_order.free_slots, s_base[bp] - f.minimizer_order.num_keys);
-            Probe pr = probe_bucket(f, pos);
-            s_base[bp] = pr.base;
-            s_step[bp] = int8_t(pr.slope);
-        }
-        if (n_retry) __syncthreads();
-    }
-
-    // ---------------------------------------------------------------- E: codes ------------------
-    // k-mer q with minimizer offset p: code = base(q + p) +/- p (partitioned_mphf.cpp:297-337);
-    // position-parallel, coalesced 8-byte stores straight to the output.
     uint64_t* out = b.codes + a.tile_out[tile];
     const bool all_valid = s_n_invalid == 0;
-    if (all_valid) {
-        // 15.5 rounds of 256 consecutive k-mers: fully unrolled, 32-bit shared-memory indexing
-        uint64_t* o = out + tid;
-        constexpr int kRounds = (kTile + kThreads - 1) / kThreads;
-#pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int q = tid + r * kThreads;
-            if (r * kThreads + kThreads <= kTile || q < kTile) {
-                const uint32_t p = s_pos[q];
-                const int bp = q + int(p);
-                const int32_t st = s_step[bp];
-                const int32_t sp = st > 0 ? int32_t(p) : -int32_t(p);
-                const uint64_t code = s_base[bp] + uint64_t(int64_t(sp));
-                if (st != 0) __stcs(o + r * kThreads, code);
-                else s_list[atomicAdd(&s_n_fb, 1u)] = uint16_t(q);  // colliding minimizer: needs the k-mer
+
+    // ---------------------------------------------------------------- D + E ----------------------
+    // One lane per distinct minimizer position: m-mer -> PTHash -> wavelet tree -> sizes_and_positions
+    // (device_mphf.cuh); then k-mer q with minimizer offset p gets base(q + p) +/- p
+    // (partitioned_mphf.cpp:297-337), position-parallel, coalesced 8-byte stores.  At most kCap
+    // probe results are held at once; denser strips (tiny windows) go round the loop again.
+    for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
+        const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
+        {
+            uint32_t word = my_word, idx = my_first;
+            while (word) {
+                int bit = __ffs(word) - 1;
+                word &= word - 1;
+                if (idx >= i0 && idx < i1) s_list[idx - i0] = uint16_t(lane * 32 + bit);
+                ++idx;
             }
         }
-    } else {
-        for (int q = tid; q < kTile; q += kThreads) {
-            const uint32_t mw = s_invalid[q >> 5];
-            if ((mw >> (q & 31)) & 1u) continue;
-            const uint32_t p = s_pos[q];
-            const int bp = q + int(p);
-            const int32_t st = s_step[bp];
-            const int32_t sp = st > 0 ? int32_t(p) : -int32_t(p);
-            const uint64_t code = s_base[bp] + uint64_t(int64_t(sp));
-            const int oidx = q - int(s_invpre[q >> 5] + __popc(mw & ((1u << (q & 31)) - 1u)));
-            if (st != 0) __stcs(out + oidx, code);
-            else s_list[atomicAdd(&s_n_fb, 1u)] = uint16_t(q);
+        __syncwarp();
+        for (uint32_t idx = i0 + lane; idx < i1; idx += 32) {
+            const int bp = s_list[idx - i0];
+            const int g = wbase + bp;  // tile-local base index of the minimizer
+            const int wi = g >> 4, r = (g & 15) * 2;
+            uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1], w2 = s_packed[wi + 2];
+            uint32_t hi = __funnelshift_l(w1, w0, r), lo = __funnelshift_l(w2, w1, r);
+            uint64_t mm = ((uint64_t(hi) << 32) | lo) >> (64 - 2 * M);
+            Probe pr = probe_minimizer(f, mm);
+            s_base[idx - i0] = pr.base;
+            s_ref[bp] = uint16_t(idx | ((pr.slope > 0 ? 1u : (pr.slope < 0 ? 2u : 0u)) << 14));
         }
-    }
-    __syncthreads();
+        __syncwarp();
+        const bool chunked = n_min > kCap;
+        if (!chunked) {
+            if (all_valid) emit_codes<false, false>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
+            else emit_codes<true, false>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
+        } else {
+            // colliding k-mers are queued in s_list, which the next chunk reuses: flush per chunk
+            emit_codes<true, true>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
+        }
+        __syncwarp();
 
-    // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
-    // (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134)
-    {
-        const uint32_t n_fb = s_n_fb;
-        for (uint32_t e = tid; e < n_fb; e += kThreads) {
-            const int q = s_list[e];
-            const int wi = q >> 4, r = (q & 15) * 2;
+        // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
+        // (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134)
+        const uint32_t n_fb = *s_n_fb;
+        for (uint32_t e = lane; e < n_fb; e += 32) {
+            const int g = wbase + s_list[e];
+            const int wi = g >> 4, r = (g & 15) * 2;
             uint32_t x[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
             uint32_t y[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], r);
-            // y[0..3] = 128-bit window starting at base q (y[0] most significant)
+            // y[0..3] = 128-bit window starting at base g (y[0] most significant)
             uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
             uint64_t klo, khi;
-            if (K <= 32) {
+            if constexpr (K <= 32) {
                 klo = top >> (64 - 2 * K);
                 khi = 0;
+                (void)bot;
             } else {
                 constexpr int sh = 128 - 2 * K;  // 2..62
                 klo = (bot >> sh) | (top << (64 - sh));
                 khi = top >> sh;
             }
-            int oidx = q;
-            if (!all_valid) {
-                uint32_t mw = s_invalid[q >> 5];
-                oidx = q - int(s_invpre[q >> 5] + __popc(mw & ((1u << (q & 31)) - 1u)));
-            }
-            out[oidx] = f.collision_base + fallback_order(f, klo, khi);
+            uint32_t mw = s_invalid[g >> 5];
+            int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
+            out[oidx] = fallback_code(f, klo, khi);
         }
+        __syncwarp();
+        if (lane == 0) *s_n_fb = 0;
+        __syncwarp();
     }
 }
 
