@@ -98,6 +98,7 @@ struct lphb_mphf {
     void* d_arena = nullptr;
     uint64_t arena_bytes = 0;
     uint64_t l2_window_bytes = 0;      // 0: persistence not available
+    float l2_hit_ratio = 1.0f;         // share of the window that may persist (carve-out / window)
     cudaStream_t l2_stream = nullptr;  // last stream the window was attached to
     bool l2_stream_set = false;
     lphb_info info{};
@@ -158,21 +159,21 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
                 int max_persist = 0, max_window = 0;
                 cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
                 cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-                uint64_t want = arena.size();
-                if (uint64_t(max_persist) < want) want = uint64_t(max_persist);
-                if (uint64_t(max_window) < want) want = uint64_t(max_window);
-                if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-                    f->l2_window_bytes = want;
-                else
+                // window = the whole image (clamped to the device's maximum window); carve-out =
+                // as much of it as may persist; hitRatio = carve-out / window so that an image
+                // larger than the carve-out does not thrash it
+                uint64_t window = arena.size();
+                if (uint64_t(max_window) < window) window = uint64_t(max_window);
+                uint64_t carve = window;
+                if (uint64_t(max_persist) < carve) carve = uint64_t(max_persist);
+                if (carve && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                    f->l2_window_bytes = window;
+                    f->l2_hit_ratio = float(double(carve) / double(window));
+                } else {
                     cudaGetLastError();
+                }
             }
             f->ws.init();
-            // collision_base = EF[none_pos_start] + w*n_maximal, evaluated once by the device's
-            // own EF code (src/partitioned_mphf.cpp:308-311)
-            launch_collision_base(f->img, reinterpret_cast<uint64_t*>(f->ws.status.p), f->ws.stream);
-            CK(cudaMemcpyAsync(f->ws.h_status, f->ws.status.p, 8, cudaMemcpyDeviceToHost, f->ws.stream));
-            CK(cudaStreamSynchronize(f->ws.stream));
-            f->img.collision_base = f->ws.h_status[0];
             lphb_info& i = f->info;
             i.k = f->img.k;
             i.m = f->img.m;
@@ -207,7 +208,7 @@ void attach_l2_window(lphb_mphf* f, cudaStream_t s) {
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = f->d_arena;
     attr.accessPolicyWindow.num_bytes = f->l2_window_bytes;
-    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitRatio = f->l2_hit_ratio;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)

@@ -84,133 +84,118 @@ const T* ImageBuilder::append(const T* src, uint64_t n, uint64_t pad_elems) {
     return reinterpret_cast<const T*>(uintptr_t(off));
 }
 
-void ImageBuilder::read_compact(Cursor& c, DevCompact& out) {
-    FileCompact fc = c.compact();
-    out.size = fc.size;
-    out.width = uint32_t(fc.width);
-    out.mask = fc.mask;
-    // two pad words: the device reads words [i, i+1] unconditionally
-    uint64_t off = (arena_.size() + 255) & ~uint64_t(255);
-    arena_.resize(off + (fc.nwords + 2) * 8, 0);
-    if (fc.nwords) std::memcpy(arena_.data() + off, fc.words, fc.nwords * 8);
-    out.bits = reinterpret_cast<const uint64_t*>(uintptr_t(off));
-}
-
-void ImageBuilder::read_ef(Cursor& c, DevEF& out, DevPrefix* fast, std::vector<uint64_t>* decoded) {
+std::vector<uint64_t> ImageBuilder::read_ef(Cursor& c) {
+    // pthash ef_sequence / lphash ef_sequence share one layout: {bit_vector high; darray1;
+    // compact_vector low} (include/ef_sequence.hpp:107-112, pthash darray.hpp:88-94).
+    // value i = ((position of the i-th set high bit) - i) << l | low[i]  (ef_sequence.hpp:77-81)
     uint64_t nbits = c.pod<uint64_t>();
     uint64_t nw;
     const uint8_t* hw = c.vec<uint64_t>(nw);
     if ((nbits + 63) / 64 > nw) throw FormatError("EF high bits shorter than declared");
-    {
-        uint64_t off = (arena_.size() + 255) & ~uint64_t(255);
-        arena_.resize(off + (nw + 2) * 8, 0);
-        if (nw) std::memcpy(arena_.data() + off, hw, nw * 8);
-        out.high = reinterpret_cast<const uint64_t*>(uintptr_t(off));
-    }
     uint64_t positions = c.pod<uint64_t>();
     uint64_t nb, ns, no;
-    const uint8_t* bi = c.vec<int64_t>(nb);
-    const uint8_t* si = c.vec<uint16_t>(ns);
-    const uint8_t* ov = c.vec<uint64_t>(no);
-    if (nb < (positions + 1023) / 1024 || ns < (positions + 31) / 32)
-        throw FormatError("darray inventories shorter than declared");
-    out.block_inv = append(reinterpret_cast<const int64_t*>(bi), nb, 1);
-    out.sub_inv = append(reinterpret_cast<const uint16_t*>(si), ns, 4);
-    out.overflow = append(reinterpret_cast<const uint64_t*>(ov), no, 1);
-    FileCompact low_view;
-    {
-        Cursor peek = c;  // the low-bits vector is parsed twice: once as a view, once into the arena
-        low_view = peek.compact();
-    }
-    read_compact(c, out.low);
-    out.n = out.low.size;
-    if (out.n != positions) throw FormatError("EF: darray positions != number of values");
-    if (!fast && !decoded) return;
-    // Decode every value once (value i = ((position of the i-th one) - i) << l | low[i],
-    // include/ef_sequence.hpp:77-81) and re-encode as prefix sectors (device_image.h).
-    if (fast) {
-        fast->sectors = nullptr;
-        fast->n = out.n;
-    }
+    c.vec<int64_t>(nb);   // darray block inventory: select is not needed once decoded
+    c.vec<uint16_t>(ns);  // subblock inventory
+    c.vec<uint64_t>(no);  // overflow positions
+    FileCompact low = c.compact();
+    if (low.size != positions) throw FormatError("EF: darray positions != number of values");
     std::vector<uint64_t> vals;
-    vals.reserve(out.n);
-    for (uint64_t wi = 0; wi < nw && vals.size() < out.n; ++wi) {
+    vals.reserve(positions);
+    for (uint64_t wi = 0; wi < nw && vals.size() < positions; ++wi) {
         uint64_t wv;
         std::memcpy(&wv, hw + 8 * wi, 8);
-        while (wv && vals.size() < out.n) {
+        while (wv && vals.size() < positions) {
             uint64_t pos = wi * 64 + uint64_t(__builtin_ctzll(wv));
             wv &= wv - 1;
             if (pos >= nbits) break;
             uint64_t i = vals.size();
-            vals.push_back(((pos - i) << low_view.width) | low_view.get(i));
+            vals.push_back(((pos - i) << low.width) | low.get(i));
         }
     }
-    if (vals.size() != out.n) throw FormatError("EF: fewer set bits than values");
-    if (decoded) *decoded = vals;
-    if (!fast) return;
-    uint64_t nsec = out.n / 32 + 1;
-    std::vector<uint64_t> sec(nsec * 4, 0);
-    for (uint64_t s0 = 0; s0 < nsec; ++s0) {
-        uint64_t first = s0 * 32;
-        uint64_t base = first < out.n ? vals[first] : (out.n ? vals[out.n - 1] : 0);
-        if (base >> 48) return;  // does not fit: keep the EF path
-        uint64_t half = 0, nib[2] = {0, 0}, top = 0;
-        for (uint64_t j = 0; j < 32; ++j) {
-            uint64_t i = first + j;
-            uint64_t d = 0;
-            if (i + 1 < out.n) {
-                if (vals[i + 1] < vals[i]) throw FormatError("EF: values not monotone");
-                d = vals[i + 1] - vals[i];
-            }
-            if (d > 63) return;  // not a sizes/positions array after all: keep the EF path
-            if (j < 16) half += d;
-            nib[j >> 4] |= (d & 15) << (4 * (j & 15));
-            top |= (d >> 4) << (2 * j);
-        }
-        sec[4 * s0] = base | (half << 48);
-        sec[4 * s0 + 1] = nib[0];
-        sec[4 * s0 + 2] = nib[1];
-        sec[4 * s0 + 3] = top;
-    }
-    fast->sectors = append(sec.data(), sec.size(), 0);
-    fast_built_ = true;
+    if (vals.size() != positions) throw FormatError("EF: fewer set bits than values");
+    return vals;
 }
 
-void ImageBuilder::read_rank(Cursor& c, DevRank& out) {
-    uint64_t nbits = c.pod<uint64_t>();
+ImageBuilder::Bits ImageBuilder::read_bits(Cursor& c) {
+    // rs_bit_vector = {u64 nbits; vec<u64> bits; vec<u64> block_rank_pairs; vec<u64> select_hints}
+    // (include/rs_bit_vector.hpp:91-96)
+    Bits out;
+    out.nbits = c.pod<uint64_t>();
     uint64_t nw, np, nh;
     const uint8_t* bw = c.vec<uint64_t>(nw);
-    c.vec<uint64_t>(np);  // block_rank_pairs: recomputed below in sector form
+    c.vec<uint64_t>(np);  // rank directory: ranks are recomputed while the buckets are walked
     c.vec<uint64_t>(nh);  // select hints: never built by the reference (quartet_wtree.cpp:51-53)
-    if ((nbits + 63) / 64 > nw) throw FormatError("bit vector shorter than declared");
-    auto word = [&](uint64_t i) -> uint64_t {
-        if (i >= nw) return 0;
-        uint64_t v;
-        std::memcpy(&v, bw + 8 * i, 8);
-        if ((i + 1) * 64 > nbits) {  // ignore anything past nbits
-            uint64_t keep = nbits > i * 64 ? nbits - i * 64 : 0;
-            v &= keep >= 64 ? ~uint64_t(0) : ((uint64_t(1) << keep) - 1);
-        }
-        return v;
+    if ((out.nbits + 63) / 64 > nw) throw FormatError("bit vector shorter than declared");
+    out.words.resize(nw + 1, 0);
+    if (nw) std::memcpy(out.words.data(), bw, nw * 8);
+    return out;
+}
+
+// One word per bucket id: what mphf::query computes from the bucket alone
+// (src/partitioned_mphf.cpp:292-339).  Buckets are walked in id order, so the ranks that
+// quartet_wtree::rank_of (src/quartet_wtree.cpp:84-99) obtains from its rank directories are
+// plain running counters here.  `sp` = decoded sizes_and_positions prefix sums.
+void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits const& max_none,
+                                 std::vector<uint64_t> const& sp) {
+    const uint64_t D = img_.distinct_minimizers;
+    const uint64_t w = img_.w, maxblock = w * img_.n_maximal;
+    const uint64_t rs = img_.right_start, ns = img_.none_sizes_start, np = img_.none_pos_start;
+    auto S = [&](uint64_t i) -> uint64_t {
+        if (i >= sp.size()) throw FormatError("sizes_and_positions index out of range");
+        return sp[i];
     };
-    // unit u covers bits [96 u, 96 u + 96); one extra unit so that rank(nbits) needs no special
-    // case (rs_bit_vector.hpp:27-29 returns num_ones there)
-    if (nbits >> 32) throw FormatError("rank bit vector longer than 2^32 bits");
-    auto word32 = [&](uint64_t i) -> uint32_t { return uint32_t(word(i >> 1) >> (32 * (i & 1))); };
-    uint64_t nunits = nbits / 96 + 2;
-    std::vector<uint32_t> units(nunits * 4, 0);
-    uint64_t ones = 0;
-    for (uint64_t u = 0; u < nunits; ++u) {
-        units[4 * u] = uint32_t(ones);
-        for (int j = 0; j < 3; ++j) {
-            uint32_t v = word32(3 * u + j);
-            units[4 * u + 1 + j] = v;
-            ones += uint64_t(__builtin_popcount(v));
+    img_.collision_base = S(np) + maxblock;  // partitioned_mphf.cpp:308-311
+    std::vector<uint64_t> e(D);
+    uint64_t n0 = 0, n1 = 0;              // zeros / ones of root seen so far
+    uint64_t r_left = 0, r_right = 0, r_max = 0, r_none = 0;
+    uint64_t max_base = 0;
+    for (uint64_t b = 0; b < D; ++b) {
+        bool msb = root.get(b);
+        uint64_t base = 0, kind = 0;
+        if (!msb) {
+            if (n0 >= left_right.nbits) throw FormatError("wavelet tree: left/right leaf too short");
+            bool lsb = left_right.get(n0++);
+            if (!lsb) {  // LEFT: g = EF[rank] + w*n_max, l = p
+                base = S(r_left++) + maxblock;
+                kind = 1;
+            } else {     // RIGHT or collision (size 0)
+                uint64_t v1 = S(rs + r_right), v2 = S(rs + r_right + 1);
+                ++r_right;
+                if (v2 == v1) {
+                    kind = 0;
+                } else {  // g = v1 + w*n_max, l = (k-m) - p
+                    base = v1 + maxblock + uint64_t(img_.k - img_.m);
+                    kind = 2;
+                }
+            }
+        } else {
+            if (n1 >= max_none.nbits) throw FormatError("wavelet tree: max/none leaf too short");
+            bool lsb = max_none.get(n1++);
+            if (!lsb) {  // MAXIMAL: g = w*rank, l = p
+                base = w * r_max++;
+                kind = 1;
+            } else {     // NONE: g = EF[none_sizes_start+rank] + w*n_max, l = diff(none_pos) - p
+                base = S(ns + r_none) + maxblock + (S(np + r_none + 1) - S(np + r_none));
+                ++r_none;
+                kind = 2;
+            }
         }
+        if (base >> 62) throw FormatError("bucket base does not fit 62 bits");
+        if (base > max_base) max_base = base;
+        // bit 63: slope +1 (else -1), bit 62: colliding minimizer
+        e[b] = (uint64_t(kind == 1) << 63) | (uint64_t(kind == 0) << 62) | base;
     }
-    out.units = reinterpret_cast<const uint4*>(append(units.data(), units.size(), 0));
-    out.nbits = nbits;
-    out.num_ones = ones;
+    img_.buckets.n = D;
+    if (max_base < (1ull << 30)) {
+        std::vector<uint32_t> e32(D);
+        for (uint64_t b = 0; b < D; ++b)
+            e32[b] = uint32_t(e[b] >> 62) << 30 | uint32_t(e[b] & 0x3FFFFFFFull);  // same two flag bits on top
+        img_.buckets.wide = 0;
+        img_.buckets.entries = append(e32.data(), D, 8);
+    } else {
+        img_.buckets.wide = 1;
+        img_.buckets.entries = append(e.data(), D, 4);
+    }
 }
 
 void reciprocal96(uint64_t d, uint32_t out[3]) {
@@ -264,35 +249,26 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
         for (uint64_t b = 0; b < nbuckets; ++b) rk[b] = uint32_t(rank_of_bucket(b));
         out.ranks = append(rk.data(), nbuckets, 4);
     }
-    out.small_divisors =
-        (out.table_size < (1ull << 32) && out.dense < (1ull << 32) && out.sparse < (1ull << 32)) ? 1 : 0;
-    std::memset(out.m_table, 0, sizeof(out.m_table));
-    std::memset(out.m_dense, 0, sizeof(out.m_dense));
-    std::memset(out.m_sparse, 0, sizeof(out.m_sparse));
-    if (out.small_divisors) {
-        reciprocal96(out.table_size, out.m_table);
-        if (out.dense) reciprocal96(out.dense, out.m_dense);
-        if (out.sparse) reciprocal96(out.sparse, out.m_sparse);
-    }
-    std::vector<uint64_t> free_vals;
-    read_ef(c, out.free_slots, nullptr, &free_vals);
-    if (out.free_slots.n != out.table_size - out.num_keys)
-        throw FormatError("single_phf: free-slot count mismatch");
+    if (out.table_size >= (1ull << 32) || out.dense >= (1ull << 32) || out.sparse >= (1ull << 32))
+        throw FormatError("single_phf: table larger than 2^32 (impossible with 64-bit PTHash hashes)");
+    reciprocal96(out.table_size, out.m_table);
+    reciprocal96(out.dense, out.m_dense);
+    reciprocal96(out.sparse, out.m_sparse);
     // minimal remap as a plain array: one load instead of an Elias-Fano select
-    out.free32 = nullptr;
-    bool fits = true;
-    for (uint64_t v : free_vals) fits = fits && v < (1ull << 32);
-    if (fits) {
-        std::vector<uint32_t> f32(free_vals.begin(), free_vals.end());
-        out.free32 = append(f32.data(), f32.size(), 4);
-        has_free32_.push_back(&out == &img_.minimizer_order ? 0 : 1);
+    std::vector<uint64_t> free_vals = read_ef(c);
+    if (free_vals.size() != out.table_size - out.num_keys)
+        throw FormatError("single_phf: free-slot count mismatch");
+    std::vector<uint32_t> f32(free_vals.size());
+    for (size_t i = 0; i < free_vals.size(); ++i) {
+        if (free_vals[i] >= out.table_size) throw FormatError("single_phf: free slot outside the table");
+        f32[i] = uint32_t(free_vals[i]);
     }
+    out.free32 = append(f32.data(), f32.size(), 4);
 }
 
 void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (kmer_bits != 64 && kmer_bits != 128) throw FormatError("kmer_bits must be 64 or 128");
     arena_.clear();
-    has_free32_.clear();
     img_ = DevImage{};
     Cursor c{data, data + n};
     img_.k = c.pod<uint8_t>();
@@ -308,56 +284,33 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (img_.m == 0 || img_.m > 31 || img_.k < img_.m || img_.k > uint32_t(kmer_bits / 2 - 1))
         throw FormatError("k/m out of range for this kmer_t");
     img_.w = img_.k - img_.m + 1;
-    img_.maximal_block = uint64_t(img_.w) * img_.n_maximal;
     read_phf(c, img_.minimizer_order);
-    read_rank(c, img_.root);
-    read_rank(c, img_.left_right);
-    read_rank(c, img_.max_none);
-    fast_built_ = false;
-    read_ef(c, img_.sp, &img_.sp_fast);
+    Bits root = read_bits(c), left_right = read_bits(c), max_none = read_bits(c);
+    std::vector<uint64_t> sp = read_ef(c);
     read_phf(c, img_.fallback);
     if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
     if (img_.minimizer_order.num_keys != img_.distinct_minimizers ||
-        img_.root.nbits != img_.distinct_minimizers ||
-        img_.left_right.nbits + img_.max_none.nbits != img_.distinct_minimizers)
+        root.nbits != img_.distinct_minimizers ||
+        left_right.nbits + max_none.nbits != img_.distinct_minimizers)
         throw FormatError("inconsistent minimizer counts");
     if (!(img_.right_start <= img_.none_sizes_start && img_.none_sizes_start <= img_.none_pos_start &&
-          img_.none_pos_start < img_.sp.n))
+          img_.none_pos_start < sp.size()))
         throw FormatError("inconsistent sizes_and_positions partition");
+    build_buckets(root, left_right, max_none, sp);
     fallback_keys_ = img_.fallback.num_keys;
     file_bytes_ = n;
     arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
 }
 
-void ImageBuilder::rebase_compact(DevCompact& c, const uint8_t* base) {
-    c.bits = reinterpret_cast<const uint64_t*>(base + uintptr_t(c.bits));
-}
-void ImageBuilder::rebase_ef(DevEF& e, const uint8_t* base) {
-    e.high = reinterpret_cast<const uint64_t*>(base + uintptr_t(e.high));
-    e.block_inv = reinterpret_cast<const int64_t*>(base + uintptr_t(e.block_inv));
-    e.sub_inv = reinterpret_cast<const uint16_t*>(base + uintptr_t(e.sub_inv));
-    e.overflow = reinterpret_cast<const uint64_t*>(base + uintptr_t(e.overflow));
-    rebase_compact(e.low, base);
-}
-void ImageBuilder::rebase_phf(DevPhf& p, const uint8_t* base, bool has_free32) {
-    if (has_free32) p.free32 = reinterpret_cast<const uint32_t*>(base + uintptr_t(p.free32));
-    p.ranks = base + uintptr_t(p.ranks);
-    p.hashed_pilots = reinterpret_cast<const uint64_t*>(base + uintptr_t(p.hashed_pilots));
-    rebase_ef(p.free_slots, base);
-}
-
 DevImage ImageBuilder::rebased(const void* device_base) const {
     DevImage d = img_;
     auto* base = static_cast<const uint8_t*>(device_base);
-    bool f0 = false, f1 = false;
-    for (int w : has_free32_) (w == 0 ? f0 : f1) = true;
-    rebase_phf(d.minimizer_order, base, f0);
-    rebase_phf(d.fallback, base, f1);
-    d.root.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.root.units));
-    d.left_right.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.left_right.units));
-    d.max_none.units = reinterpret_cast<const uint4*>(base + uintptr_t(d.max_none.units));
-    rebase_ef(d.sp, base);
-    if (fast_built_) d.sp_fast.sectors = reinterpret_cast<const uint64_t*>(base + uintptr_t(d.sp_fast.sectors));
+    for (DevPhf* p : {&d.minimizer_order, &d.fallback}) {
+        p->free32 = reinterpret_cast<const uint32_t*>(base + uintptr_t(p->free32));
+        p->ranks = base + uintptr_t(p->ranks);
+        p->hashed_pilots = reinterpret_cast<const uint64_t*>(base + uintptr_t(p->hashed_pilots));
+    }
+    d.buckets.entries = base + uintptr_t(d.buckets.entries);
     return d;
 }
 

@@ -39,20 +39,22 @@ private:
     struct Cursor;
     template <class T>
     const T* append(const T* src, uint64_t n, uint64_t pad_elems = 0);
-    void read_compact(Cursor& c, DevCompact& out);
-    // decoded (optional): receives every value of the sequence
-    void read_ef(Cursor& c, DevEF& out, DevPrefix* fast = nullptr, std::vector<uint64_t>* decoded = nullptr);
-    void read_rank(Cursor& c, DevRank& out);
+    // every value of a serialized Elias-Fano sequence (pthash layout), decoded
+    std::vector<uint64_t> read_ef(Cursor& c);
+    // the bits of a serialized rs_bit_vector (rank directory skipped)
+    struct Bits {
+        uint64_t nbits = 0;
+        std::vector<uint64_t> words;
+        bool get(uint64_t i) const { return (words[i >> 6] >> (i & 63)) & 1; }
+    };
+    Bits read_bits(Cursor& c);
     void read_phf(Cursor& c, DevPhf& out);
-    static void rebase_compact(DevCompact& c, const uint8_t* base);
-    static void rebase_ef(DevEF& e, const uint8_t* base);
-    static void rebase_phf(DevPhf& p, const uint8_t* base, bool has_free32);
+    void build_buckets(Bits const& root, Bits const& left_right, Bits const& max_none,
+                       std::vector<uint64_t> const& sp);
 
     std::vector<uint8_t> arena_;
     DevImage img_{};
     uint64_t fallback_keys_ = 0, file_bytes_ = 0;
-    bool fast_built_ = false;
-    std::vector<int> has_free32_;  // 0: minimizer_order, 1: fallback
 };
 
 // ceil(2^96 / d) as three 32-bit limbs (d >= 1, d < 2^32); limbs all zero for d == 1.

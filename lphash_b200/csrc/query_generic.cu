@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(256) k_query_generic(const __grid_constant__ D
             if (p == 0 || h < best_h) { best_h = h; best_mm = mm; best_p = p; }
         }
         Probe pr = probe_minimizer(f, best_mm);
-        uint64_t hval = pr.type == T_COLLISION ? pr.base + fallback_order(f, lo, hi)
-                                               : probe_hval(pr, best_p);
+        uint64_t hval = pr.slope == 0 ? pr.base + fallback_order(f, lo, hi) : probe_hval(pr, best_p);
         b.codes[__ldg(b.code_off + c) + (i - start)] = hval;
     }
 }
@@ -119,7 +118,7 @@ __global__ void k_query_quirk(const __grid_constant__ DevImage f, const char* ba
     uint64_t mmer = 0, lo = 0, hi = 0, run = 0;
     // last probe context (mm_context_t, partitioned_mphf.hpp:55-60)
     uint64_t g_rank = 0, l_rank = 0;
-    uint32_t ctx_type = 0;
+    int32_t ctx_slope = 1;  // slope of the last probe (0: colliding minimizer); MAXIMAL before any
     for (uint64_t i = 0; i < len; ++i) {
         uint32_t code = nt4(uint8_t(s[i]));
         if (code > 3) { run = 0; cursor = 0; continue; }
@@ -141,9 +140,9 @@ __global__ void k_query_quirk(const __grid_constant__ DevImage f, const char* ba
         }
         if (action == 0) {
             if (run >= k) {
-                if (ctx_type == T_COLLISION) l_rank = fallback_order(f, lo, hi);
-                else if (ctx_type == T_RIGHT || ctx_type == T_NONE) ++l_rank;
-                else --l_rank;
+                if (ctx_slope == 0) l_rank = fallback_order(f, lo, hi);
+                else if (ctx_slope < 0) ++l_rank;  // RIGHT, NONE
+                else --l_rank;                     // LEFT, MAXIMAL
                 dst[n_out++] = g_rank + l_rank;
             }
         } else {
@@ -157,10 +156,10 @@ __global__ void k_query_quirk(const __grid_constant__ DevImage f, const char* ba
                     if (ring_h[min_slot] > ring_h[q]) { min_slot = q; p1 = step; }
             }
             Probe pr = probe_minimizer(f, ring_mm[min_slot]);
-            ctx_type = pr.type;
+            ctx_slope = pr.slope;
             // split hval back into the reference's (global_rank, local_rank) so that the
             // +-1 continuation above reproduces :131-145 (mod 2^64)
-            if (pr.type == T_COLLISION) { g_rank = pr.base; l_rank = fallback_order(f, lo, hi); }
+            if (pr.slope == 0) { g_rank = pr.base; l_rank = fallback_order(f, lo, hi); }
             else if (pr.slope > 0) { g_rank = pr.base; l_rank = p1; }
             else { g_rank = pr.base; l_rank = uint64_t(0) - uint64_t(p1); }
             dst[n_out++] = g_rank + l_rank;
@@ -191,10 +190,6 @@ __global__ void k_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long lo
         local += dirty[c] ? 1 : 0;
     for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(status + 1, local);
-}
-
-__global__ void k_collision_base(const __grid_constant__ DevImage f, uint64_t* out) {
-    *out = ef_access(f.sp, f.none_pos_start) + f.maximal_block;
 }
 
 }  // namespace
@@ -252,10 +247,6 @@ void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* st
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148ull * 8) blocks = 148ull * 8;
     k_count_dirty<<<unsigned(blocks), 256, 0, stream>>>(dirty, n, status);
-}
-
-void launch_collision_base(DevImage const& img, uint64_t* d_out, cudaStream_t stream) {
-    k_collision_base<<<1, 1, 0, stream>>>(img, d_out);
 }
 
 }  // namespace lphb

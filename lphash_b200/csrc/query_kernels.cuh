@@ -53,7 +53,4 @@ void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src
 void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status,
                         cudaStream_t stream);
 
-// One-thread kernel computing collision_base = EF[none_pos_start] + w * n_maximal.
-void launch_collision_base(DevImage const& img, uint64_t* d_out, cudaStream_t stream);
-
 }  // namespace lphb

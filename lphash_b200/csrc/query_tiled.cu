@@ -9,19 +9,24 @@
 //                 bytes flag their contig dirty (it is then recomputed by the exact sequential
 //                 kernel).  Warp 0 meanwhile rasterises contig seams into a
 //                 bitmask of invalid k-mer starts.
-//  B  scan        each thread owns 16 consecutive k-mer starts: 16 m-mer hashes from registers
-//                 (MurmurHash2-64, seeded), the W-1 it lacks from lane+1 by warp shuffle (lane 31
-//                 only feeds lane 30: warps overlap by one lane), van Herk / Gil-Werman sliding
-//                 minimum with leftmost ties -> minimizer offset p of every k-mer, and a 16-bit
-//                 mask of super-k-mer heads (minimizer occurrence differs from the predecessor's).
-//  C  compact     heads of the CTA -> dense list in shared memory (warp scan + per-thread loop).
-//  D  probe       one thread per head: minimizer m-mer -> PTHash -> wavelet tree -> Elias-Fano
-//                 (device_mphf.cuh) -> the head's hash code and the run's slope are left in the
-//                 head's own staging slot.
-//  E  fill+store  each thread walks its 16 k-mers: code = previous -/+ 1 inside a super-k-mer
-//                 (partitioned_mphf.hpp:131-145), reload at heads; colliding runs are queued and
-//                 resolved densely through fallback_kmer_order; codes leave through a padded
-//                 shared-memory transpose as fully coalesced 8-byte stores.
+//  B  scan        each thread owns 16 consecutive k-mer starts.  16 m-mer hashes from registers
+//                 (MurmurHash2-64, seeded); each is reduced to a 32-bit key = top 27 bits of the
+//                 hash | 5-bit thread-local position, so that ONE unsigned min picks the smaller
+//                 hash and, between equal keys, the leftmost.  The W-1 keys a thread lacks come
+//                 from lane+1 by warp shuffle (lane 31 only feeds lane 30: warps overlap by one
+//                 lane).  Sliding minimum = sparse table of 3-input minima (VIMNMX3): spans of 3,
+//                 9, then two spans cover the window.  A second pass with the position bits
+//                 complemented finds the RIGHTMOST minimum; if the two differ anywhere the 27-bit
+//                 keys tied (true repeat or truncation tie) and that thread recomputes its 16
+//                 windows from the full 64-bit hashes (out of line, rare).  Result: minimizer
+//                 offset of every k-mer + mask of positions that are some k-mer's minimizer.
+//  C  compact     minimizer positions of the warp -> dense list in shared memory (warp scan).
+//  D  probe       one lane per distinct minimizer position: m-mer -> PTHash -> bucket table
+//                 (device_mphf.cuh) -> {B, ns} with  code(k-mer at q) = B + ns * q.
+//  E  emit        position-parallel: lane l handles k-mers l, l+32, ...: two byte loads find the
+//                 entry, one IMAD.WIDE makes the code, 8-byte stores are fully coalesced.
+//                 K-mers of colliding minimizers are queued and resolved through
+//                 fallback_kmer_order (partitioned_mphf.cpp:308-313).
 //
 // Every k-mer's code is a pure function of its own k bases, so tiles only share
 // k-1 bases of read overlap and nothing else.
@@ -47,8 +52,13 @@ constexpr int kMaskWords = kTile / 32;         // 124
 constexpr int kMaskSlots = kMaskWords + 1;
 constexpr int kWarpSlots = kWarpKmers + 32;    // positions a minimizer of the warp's k-mers can sit at
 constexpr int kWarpMaskWords = kWarpSlots / 32;  // 32: one word per lane
-constexpr int kCap = 256;                      // probe results held at once per warp
-constexpr int kWarpBytes = kWarpSlots * (1 + 2 + 2) + kCap * 8 + (kWarpMaskWords + 4) * 4;
+constexpr int kProbes = 6;                     // probes a lane keeps in flight
+constexpr int kCap = 32 * kProbes;             // probe results held at once per warp (index fits a byte)
+struct Entry {                                 // code of the k-mer at warp-local q = B + ns * q (mod 2^64)
+    uint32_t lo;                               // low word of B (the high word lives in s_hi)
+    int32_t ns;                                // -1: LEFT/MAXIMAL, +1: RIGHT/NONE, 0: colliding minimizer
+};
+constexpr int kWarpBytes = kCap * (8 + 4) + kWarpSlots * (1 + 1 + 2) + (kWarpMaskWords + 4 + 16) * 4;
 constexpr int kPackedSlots = 256;
 constexpr int kSmemBytes = kWarps * kWarpBytes + kPackedSlots * 4 + kMaskSlots * (4 + 2) + 16;
 static_assert(kWarpMaskWords == 32 && kWarpBytes % 16 == 0, "per-warp layout");
@@ -103,42 +113,165 @@ template <int K, int M>
 struct Cfg {
     static constexpr int W = K - M + 1;
     static constexpr int NW = (kS + K - 1 + 15) / 16;        // packed words a thread reads
-    static constexpr int NH = kS + W - 1;                    // hashes a thread needs
+    static constexpr int NH = kS + W - 1;                    // m-mers under a thread's 16 windows
     static constexpr int TileWords = kTile / 16 + NW;        // words staged per tile
     static_assert(W >= 1 && W <= 17, "tiled kernel: window must fit one shuffle hop");
+    static_assert(NH <= 32, "thread-local minimizer positions must fit the 5-bit key field");
     static_assert(M <= 31 && K <= 63, "k, m out of range");
     static_assert(TileWords <= kPackedSlots, "packed tile must fit its shared-memory array");
 };
 
-// Codes of the k-mers [q0, q1) of a warp whose minimizers are list entries [i0, i1) (their probe
-// results sit in s_base[0 .. i1-i0)).  `checked` = some starts of the tile produce no code.
-template <bool kChecked, bool kChunked>
-__device__ __forceinline__ void emit_codes(int lane, int wbase, uint32_t i0, uint32_t i1,
-                                           const uint8_t* s_pos, const uint16_t* s_ref,
-                                           const uint64_t* s_base, uint16_t* s_list,
-                                           uint32_t* s_n_fb, const uint32_t* s_invalid,
-                                           const uint16_t* s_invpre, uint64_t* out) {
-    uint64_t* o = out + wbase + lane;
-#pragma unroll 4
+// a * 0xc6a4a7935bd1e995 mod 2^64 in three multiply-adds (IMAD.WIDE + 2 IMAD, all on the FMA pipe)
+__device__ __forceinline__ uint64_t mul_murmur(uint32_t lo, uint32_t hi) {
+    uint64_t w = uint64_t(lo) * 0x5bd1e995u;
+    uint32_t h = uint32_t(w >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(lo), "r"(0xc6a4a793u));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(hi), "r"(0x5bd1e995u));
+    return (uint64_t(h) << 32) | uint32_t(w);
+}
+__device__ __forceinline__ uint64_t mul_murmur(uint64_t a) { return mul_murmur(uint32_t(a), uint32_t(a >> 32)); }
+
+// 16 bases starting at base t (compile-time after unrolling) of a thread's packed words
+template <int NW>
+__device__ __forceinline__ uint32_t win16(const uint32_t (&wds)[NW], int t) {
+    const int q = t >> 4, r = (t & 15) * 2;
+    if (r == 0) return wds[q];
+    const uint32_t nxt = q + 1 < NW ? wds[q + 1] : 0u;
+    return __funnelshift_l(nxt, wds[q], r);
+}
+
+// out[i] = min(k[i .. i+W-1]) for i < 16: sparse table of 3-input minima (spans 3, 9), the window
+// is then covered by two (overlapping) spans.  Unused table entries vanish at compile time.
+template <int W, int NH>
+__device__ __forceinline__ void window_min(const uint32_t (&k)[NH], uint32_t (&out)[kS]) {
+    if constexpr (W == 1) {
+#pragma unroll
+        for (int i = 0; i < kS; ++i) out[i] = k[i];
+    } else if constexpr (W == 2) {
+#pragma unroll
+        for (int i = 0; i < kS; ++i) out[i] = min(k[i], k[i + 1]);
+    } else {
+        uint32_t m3[NH];
+#pragma unroll
+        for (int i = 0; i + 2 < NH; ++i) m3[i] = __vimin3_u32(k[i], k[i + 1], k[i + 2]);
+        if constexpr (W == 3) {
+#pragma unroll
+            for (int i = 0; i < kS; ++i) out[i] = m3[i];
+        } else if constexpr (W <= 6) {
+#pragma unroll
+            for (int i = 0; i < kS; ++i) out[i] = min(m3[i], m3[i + W - 3]);
+        } else if constexpr (W < 9) {
+#pragma unroll
+            for (int i = 0; i < kS; ++i) out[i] = __vimin3_u32(m3[i], m3[i + 3], m3[i + W - 3]);
+        } else {
+            uint32_t m9[NH];
+#pragma unroll
+            for (int i = 0; i + 8 < NH; ++i) m9[i] = __vimin3_u32(m3[i], m3[i + 3], m3[i + 6]);
+            if constexpr (W == 9) {
+#pragma unroll
+                for (int i = 0; i < kS; ++i) out[i] = m9[i];
+            } else if constexpr (W <= 12) {
+#pragma unroll
+                for (int i = 0; i < kS; ++i) out[i] = min(m9[i], m3[i + W - 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kS; ++i) out[i] = min(m9[i], m9[i + W - 9]);
+            }
+        }
+    }
+}
+
+// m-mer starting at tile-local base g, from the packed tile in shared memory
+template <int M>
+__device__ __forceinline__ uint64_t mmer_at(const uint32_t* s_packed, int g) {
+    const int wi = g >> 4, r = (g & 15) * 2;
+    const uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1], w2 = s_packed[wi + 2];
+    const uint32_t hi = __funnelshift_l(w1, w0, r), lo = __funnelshift_l(w2, w1, r);
+    return ((uint64_t(hi) << 32) | lo) >> (64 - 2 * M);
+}
+
+// Exact minimizer offsets of the 16 k-mers starting at tile-local base g0, from the full 64-bit
+// hashes (strict '<' keeps the leftmost on ties: partitioned_mphf.hpp:124,152,159).  Taken only by
+// threads whose 27-bit keys tied; out of line.  Returns the mask of minimizer positions.
+template <int K, int M>
+static __device__ __noinline__ uint32_t exact_strip(const uint32_t* s_packed, int g0, uint64_t seed,
+                                                    uint8_t* pos_out) {
+    constexpr int W = K - M + 1, NH = kS + W - 1;
+    uint64_t h[NH];
+#pragma unroll 1
+    for (int j = 0; j < NH; ++j) h[j] = murmur64(mmer_at<M>(s_packed, g0 + j), seed);
+    uint32_t marks = 0;
+#pragma unroll 1
+    for (int i = 0; i < kS; ++i) {
+        int best = i;
+        for (int j = i + 1; j < i + W; ++j)
+            if (h[j] < h[best]) best = j;
+        pos_out[i] = uint8_t(best);
+        marks |= 1u << best;
+    }
+    return marks;
+}
+
+// Codes of the k-mers of a warp, position-parallel: lane l handles k-mers l, l+32, ...; two byte
+// loads find the entry of the k-mer's minimizer, code = B + ns * q, coalesced 8-byte stores.
+//
+// Plain form, for a warp whose 992 starts all yield a code, whose entries share the high word
+// `hi` of B and cannot carry out of the low word (1024 <= lo < 2^32 - 1024), with no colliding
+// minimizer and a single chunk: one 32-bit multiply-add per code.
+__device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
+                                           const Entry* s_ent, uint32_t hi, uint64_t* out_warp) {
+    const uint8_t* pos_l = s_pos + lane;
+    const uint8_t* ref_l = s_ref + (lane & 16);
+    uint2* o = reinterpret_cast<uint2*>(out_warp + lane);
+#pragma unroll 8
+    for (int r = 0; r < kWarpKmers / 32; ++r) {
+        const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) warp-local position of the minimizer
+        const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
+        uint32_t lo;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
+        __stcs(o + r * 32, make_uint2(lo, hi));
+    }
+}
+
+// General form.  Per group of 32 starts the (warp-uniform) word of the invalid-start mask tells
+// whether starts without a code (contig seams) must be skipped and the output index compacted;
+// k-mers of colliding minimizers are queued in s_list; kChunked (more than kCap minimizers):
+// entries outside [i0, i1) are left to their own chunk.
+template <bool kChunked>
+__device__ __forceinline__ void emit_general(int lane, int wbase, uint32_t i0, uint32_t i1,
+                                             const uint8_t* s_pos, const uint8_t* s_ref,
+                                             const uint32_t* s_minmask, const uint16_t* s_wpre,
+                                             const Entry* s_ent, const uint32_t* s_hi,
+                                             uint16_t* s_list, uint32_t* s_n_fb,
+                                             const uint32_t* s_invalid, const uint16_t* s_invpre,
+                                             uint64_t* out) {
+    const int lane16 = lane & 16;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t* inv = s_invalid + (wbase >> 5);  // wbase is a multiple of 32
+    const uint16_t* pre = s_invpre + (wbase >> 5);
+    uint64_t* out_l = out + wbase + lane;
+#pragma unroll 2
     for (int r = 0; r < kWarpKmers / 32; ++r) {
         const int q = lane + r * 32;
-        const uint32_t p = s_pos[q];
-        const uint32_t ref = s_ref[q + int(p)];
-        const uint32_t idx = ref & 0x3FFFu, kind = ref >> 14;  // kind 1: +p, 2: -p, 0: collision
-        if (kChunked && (idx < i0 || idx >= i1)) continue;
-        const int32_t sp = kind == 1 ? int32_t(p) : -int32_t(p);
-        const uint64_t code = s_base[idx - i0] + uint64_t(int64_t(sp));
-        if (!kChecked) {
-            if (kind != 0) __stcs(o + r * 32, code);
-            else s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);  // colliding minimizer: needs the k-mer
+        const uint32_t mw = inv[r];  // uniform in the warp
+        if ((mw >> lane) & 1u) continue;
+        const int mp = int(s_pos[q]) + lane16 + r * 32;  // warp-local position of q's minimizer
+        uint32_t idx;
+        if (kChunked) {  // global list index of position mp: rank among the marked positions
+            idx = s_wpre[mp >> 5] + __popc(s_minmask[mp >> 5] & ((1u << (mp & 31)) - 1u));
+            if (idx < i0 || idx >= i1) continue;
+            idx -= i0;
         } else {
-            const int g = wbase + q;
-            const uint32_t mw = s_invalid[g >> 5];
-            if ((mw >> (g & 31)) & 1u) continue;
-            const int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
-            if (kind != 0) __stcs(out + oidx, code);
-            else s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);
+            idx = s_ref[mp];
         }
+        const Entry e = s_ent[idx];
+        if (e.ns == 0) {  // colliding minimizer: needs the k-mer itself
+            s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);
+            continue;
+        }
+        const uint64_t B = (uint64_t(s_hi[idx]) << 32) | e.lo;
+        const uint64_t code = B + uint64_t(int64_t(e.ns) * int64_t(q));
+        __stcs(out_l + (r * 32 - int(pre[r]) - __popc(mw & lt)), code);
     }
 }
 
@@ -148,23 +281,23 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
     constexpr int W = C::W, NW = C::NW, NH = C::NH;
-    static_assert(NH <= 32, "per-thread minimizer marks must fit one 32-bit mask");
 
     // dynamic shared memory: one private region per warp (warp-local coordinates) + tile-wide
     // packed bases and invalid-start bitmask
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char* mine = smem_raw + warp * kWarpBytes;
-    uint64_t* s_base = reinterpret_cast<uint64_t*>(mine);                  // per probe (list index): result
-    uint8_t* s_pos = reinterpret_cast<uint8_t*>(s_base + kCap);            // per k-mer: minimizer offset p
-    uint16_t* s_ref = reinterpret_cast<uint16_t*>(s_pos + kWarpSlots);     // per position: list index | kind << 14
-    uint16_t* s_list = s_ref + kWarpSlots;                                 // minimizer positions (chunk); later colliding k-mers (<= kWarpKmers)
+    Entry* s_ent = reinterpret_cast<Entry*>(mine);                          // per probe (list index)
+    uint32_t* s_hi = reinterpret_cast<uint32_t*>(s_ent + kCap);            // per probe: high word of B
+    uint8_t* s_pos = reinterpret_cast<uint8_t*>(s_hi + kCap);              // per k-mer: thread-local minimizer position
+    uint8_t* s_ref = s_pos + kWarpSlots;                                   // per position: chunk-local list index
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_ref + kWarpSlots);    // minimizer positions (chunk); later colliding k-mers
     uint32_t* s_minmask = reinterpret_cast<uint32_t*>(s_list + kWarpSlots);  // bit b: position b is some k-mer's minimizer
     uint32_t* s_n_fb = s_minmask + kWarpMaskWords;                         // colliding k-mers queued
+    uint16_t* s_wpre = reinterpret_cast<uint16_t*>(s_n_fb + 4);            // per mask word: marked positions before it
     uint32_t* s_packed = reinterpret_cast<uint32_t*>(smem_raw + kWarps * kWarpBytes);  // 2-bit bases (tile)
     uint32_t* s_invalid = s_packed + kPackedSlots;     // bit q: k-mer start q produces no code (tile)
     uint16_t* s_invpre = reinterpret_cast<uint16_t*>(s_invalid + kMaskSlots);  // invalid starts before word
-    __shared__ uint32_t s_n_invalid;
 
     const uint32_t tile = blockIdx.x;
     const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
@@ -250,12 +383,14 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             if (wd < kMaskSlots) s_invpre[wd] = uint16_t(run);
             run += cnt[j];
         }
-        if (lane == 31) s_n_invalid = inc;
     }
     __syncthreads();  // invalid-start mask ready; from here on every warp runs on its own
 
     // ---------------------------------------------------------------- B: per-thread scan --------
     const int wbase = warp * kWarpKmers;  // tile-local position of this warp's first k-mer
+    const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
+    uint32_t keymask;  // ~31 held in a register so that (hash & ~31) | position is one LOP3
+    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(keymask));
 #pragma unroll 1
     for (int strip = 0; strip < kStrips; ++strip) {
         const int lseg = strip * kStrip + lane * kS;  // warp-local position of this thread's first k-mer
@@ -263,65 +398,61 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
 #pragma unroll
         for (int j = 0; j < NW; ++j) wds[j] = s_packed[((wbase + lseg) >> 4) + j];
 
-        uint64_t h[NH];
+        // keys: top 27 bits of the m-mer's hash | thread-local position (own: 0..15, the W-1
+        // received from lane+1: 16..)
+        uint32_t key[NH];
 #pragma unroll
         for (int j = 0; j < kS; ++j) {
-            // m-mer starting at base j of the thread's window: top 2M bits of the 64-bit window at j
-            const int q = j >> 4, r = (j & 15) * 2;
-            uint32_t hi = r ? __funnelshift_l(wds[q + 1], wds[q], r) : wds[q];
-            uint32_t lo;
-            if (q + 2 < NW) lo = r ? __funnelshift_l(wds[q + 2], wds[q + 1], r) : wds[q + 1];
-            else lo = wds[q + 1] << r;
-            uint64_t win = (uint64_t(hi) << 32) | lo;
-            h[j] = murmur64(win >> (64 - 2 * M), f.mm_seed);
+            uint32_t v_lo, v_hi;
+            if constexpr (M <= 16) {
+                v_lo = M == 16 ? win16<NW>(wds, j) : win16<NW>(wds, j) >> (32 - 2 * M);
+                v_hi = 0;
+            } else {
+                v_lo = win16<NW>(wds, j + M - 16);
+                v_hi = win16<NW>(wds, j) >> (64 - 2 * M);
+            }
+            // MurmurHash2-64 (device_mphf.cuh: murmur64) up to its last multiply: the final
+            // h ^= h >> 47 cannot change the top 32 bits
+            uint64_t x = M <= 16 ? uint64_t(v_lo) * kMurmurM : mul_murmur(v_lo, v_hi);
+            x ^= x >> 47;
+            x = mul_murmur(x);
+            uint64_t h = mul_murmur(h0 ^ x);
+            h ^= h >> 47;
+            h = mul_murmur(h);
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
         }
 #pragma unroll
-        for (int j = 0; j < W - 1; ++j) h[kS + j] = __shfl_down_sync(0xFFFFFFFFu, h[j], 1);
+        for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
 
-        // van Herk / Gil-Werman over blocks of W hashes: window i = [i, i+W-1] is the suffix of
-        // its block from i joined with the prefix of the next block up to i+W-1.  Leftmost wins
-        // ties (strict comparisons, partitioned_mphf.hpp:124,152,159).  Fully unrolled with
-        // compile-time indices: suf/pre live in registers and unused entries vanish.
-        uint64_t suf_h[NH], pre_h[NH];
-        uint32_t suf_p[NH], pre_p[NH];
+        uint32_t mn[kS];
+        window_min<W, NH>(key, mn);
+        // same windows with the position bits complemented: the minimum is now the RIGHTMOST one
+        // among equal 27-bit keys; both agree on every window <=> no two candidates tied
+        uint32_t agree = 31u;
+        {
+            uint32_t rkey[NH], rmn[kS];
 #pragma unroll
-        for (int j = NH - 1; j >= 0; --j) {
-            if (j % W == W - 1 || j == NH - 1) {
-                suf_h[j] = h[j];
-                suf_p[j] = j;
-            } else {
-                bool keep = h[j] <= suf_h[j + 1];  // element j is to the left: it wins ties
-                suf_h[j] = keep ? h[j] : suf_h[j + 1];
-                suf_p[j] = keep ? uint32_t(j) : suf_p[j + 1];
-            }
-        }
+            for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ 31u;
+            window_min<W, NH>(rkey, rmn);
 #pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            if (j % W == 0) {
-                pre_h[j] = h[j];
-                pre_p[j] = j;
-            } else {
-                bool take = h[j] < pre_h[j - 1];  // element j is to the right: strictly smaller only
-                pre_h[j] = take ? h[j] : pre_h[j - 1];
-                pre_p[j] = take ? uint32_t(j) : pre_p[j - 1];
-            }
+            for (int i = 0; i < kS; ++i) agree &= mn[i] ^ rmn[i];
         }
-        uint32_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
-        uint32_t pk[4] = {0, 0, 0, 0};
+        if (lane < kLanes) {  // lane 31 only feeds keys to lane 30
+            uint32_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
+            if (agree == 31u) {
+                uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < kS; ++i) {
-            uint32_t bpos;
-            if (i % W == 0) {
-                bpos = suf_p[i];
+                for (int i = 0; i < kS; ++i) marks |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint32_t t0 = __byte_perm(mn[4 * g4], mn[4 * g4 + 1], 0x0040);
+                    uint32_t t1 = __byte_perm(mn[4 * g4 + 2], mn[4 * g4 + 3], 0x0040);
+                    pk[g4] = __byte_perm(t0, t1, 0x5410) & 0x1F1F1F1Fu;
+                }
+                *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             } else {
-                bool take = pre_h[i + W - 1] < suf_h[i];
-                bpos = take ? pre_p[i + W - 1] : suf_p[i];
+                marks = exact_strip<K, M>(s_packed, wbase + lseg, f.mm_seed, s_pos + lseg);
             }
-            marks |= 1u << bpos;
-            pk[i >> 2] |= (bpos - i) << (8 * (i & 3));
-        }
-        if (lane < kLanes) {  // lane 31 only feeds hashes to lane 30
-            *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             // lseg is a multiple of 16: the 32 local positions straddle at most two mask words
             const int sh = lseg & 16;
             atomicOr(&s_minmask[lseg >> 5], marks << sh);
@@ -331,7 +462,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     __syncwarp();
 
     // ---------------------------------------------------------------- C: rank the minimizers ----
-    // lane l owns mask word l: list index of every marked position -> s_ref
+    // lane l owns mask word l: list index of every marked position
     uint32_t my_word = s_minmask[lane];
     uint32_t n_mine = __popc(my_word);
     uint32_t inc = n_mine;
@@ -342,15 +473,14 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     }
     const uint32_t n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
     const uint32_t my_first = inc - n_mine;
+    s_wpre[lane] = uint16_t(my_first);
 
     uint64_t* out = b.codes + a.tile_out[tile];
-    const bool all_valid = s_n_invalid == 0;
+    const bool chunked = n_min > kCap;
+    // does any start of this warp's range yield no code?  (31 mask words, one per lane)
+    const bool warp_has_invalid = __any_sync(0xFFFFFFFFu, lane < kWarpKmers / 32 && s_invalid[(wbase >> 5) + lane] != 0);
 
     // ---------------------------------------------------------------- D + E ----------------------
-    // One lane per distinct minimizer position: m-mer -> PTHash -> wavelet tree -> sizes_and_positions
-    // (device_mphf.cuh); then k-mer q with minimizer offset p gets base(q + p) +/- p
-    // (partitioned_mphf.cpp:297-337), position-parallel, coalesced 8-byte stores.  At most kCap
-    // probe results are held at once; denser strips (tiny windows) go round the loop again.
     for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
         const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
         {
@@ -363,26 +493,74 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             }
         }
         __syncwarp();
-        for (uint32_t idx = i0 + lane; idx < i1; idx += 32) {
-            const int bp = s_list[idx - i0];
-            const int g = wbase + bp;  // tile-local base index of the minimizer
-            const int wi = g >> 4, r = (g & 15) * 2;
-            uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1], w2 = s_packed[wi + 2];
-            uint32_t hi = __funnelshift_l(w1, w0, r), lo = __funnelshift_l(w2, w1, r);
-            uint64_t mm = ((uint64_t(hi) << 32) | lo) >> (64 - 2 * M);
-            Probe pr = probe_minimizer(f, mm);
-            s_base[idx - i0] = pr.base;
-            s_ref[bp] = uint16_t(idx | ((pr.slope > 0 ? 1u : (pr.slope < 0 ? 2u : 0u)) << 14));
+        // kProbes probes per lane in flight: the dependent gathers (pilot rank -> hashed pilot ->
+        // [free slot] -> bucket word) of different probes overlap instead of queueing up
+        bool special = false, have = false;
+        uint32_t hi0 = 0;
+        {
+            const DevPhf& P = f.minimizer_order;
+            const uint32_t nu = (i1 - i0 + 31) >> 5;  // 32-probe groups in this chunk (uniform)
+            int bp[kProbes];
+            uint64_t h[kProbes];
+            uint32_t slot[kProbes];
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u) {
+                if (u < nu) {
+                    const uint32_t li = lane + 32 * u;
+                    bp[u] = s_list[li < i1 - i0 ? li : 0];  // dead lanes redo entry 0 (harmless)
+                    h[u] = murmur64(mmer_at<M>(s_packed, wbase + bp[u]), P.seed);
+                    slot[u] = phf_bucket(P, h[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u)
+                if (u < nu) slot[u] = phf_pilot_rank(P, slot[u]);
+            uint64_t hp[kProbes];
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u)
+                if (u < nu) hp[u] = __ldg(P.hashed_pilots + slot[u]);
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u)
+                if (u < nu) slot[u] = phf_table_slot(P, h[u] ^ hp[u]);
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u)
+                if (u < nu && slot[u] >= uint32_t(P.num_keys)) slot[u] = __ldg(P.free32 + (slot[u] - uint32_t(P.num_keys)));
+            // bucket word -> {B, ns}: hval = base + slope * (bp - q) = (base + slope * bp) + (-slope) * q
+            uint64_t word[kProbes];
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u) {
+                if (u < nu) {
+                    if (f.buckets.wide) word[u] = __ldg(reinterpret_cast<const uint64_t*>(f.buckets.entries) + slot[u]);
+                    else word[u] = __ldg(reinterpret_cast<const uint32_t*>(f.buckets.entries) + slot[u]);
+                }
+            }
+            const int fsh = f.buckets.wide ? 62 : 30;
+            const uint64_t bmask = (uint64_t(1) << fsh) - 1;
+#pragma unroll
+            for (int u = 0; u < kProbes; ++u) {
+                const uint32_t li = lane + 32 * u;
+                if (u < nu && li < i1 - i0) {
+                    const uint32_t flags = uint32_t(word[u] >> fsh);  // bit 1: slope +1, bit 0: colliding
+                    const int32_t ns = (flags & 1u) ? 0 : ((flags & 2u) ? -1 : 1);
+                    const uint64_t B = (word[u] & bmask) - uint64_t(int64_t(ns) * bp[u]);
+                    const uint32_t lo = uint32_t(B), hi = uint32_t(B >> 32);
+                    if (u == 0) { hi0 = hi; have = true; }
+                    special |= ns == 0 || hi != hi0 || lo - 1024u >= 0xFFFFF800u;  // needs 64-bit care
+                    s_ent[li] = Entry{lo, ns};
+                    s_hi[li] = hi;
+                    s_ref[bp[u]] = uint8_t(li);
+                }
+            }
         }
+        // plain emit needs: every entry of the warp shares lane 0's high word and cannot carry, no
+        // colliding minimizer, no start without a code in the warp's range, one chunk
+        const uint32_t hi_warp = __shfl_sync(0xFFFFFFFFu, hi0, 0);
+        special |= have && hi0 != hi_warp;
+        const bool plain = !chunked && !warp_has_invalid && !__any_sync(0xFFFFFFFFu, special);
         __syncwarp();
-        const bool chunked = n_min > kCap;
-        if (!chunked) {
-            if (all_valid) emit_codes<false, false>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
-            else emit_codes<true, false>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
-        } else {
-            // colliding k-mers are queued in s_list, which the next chunk reuses: flush per chunk
-            emit_codes<true, true>(lane, wbase, i0, i1, s_pos, s_ref, s_base, s_list, s_n_fb, s_invalid, s_invpre, out);
-        }
+        if (plain) emit_plain(lane, s_pos, s_ref, s_ent, hi_warp, out + wbase - s_invpre[wbase >> 5]);
+        else if (!chunked) emit_general<false>(lane, wbase, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_list, s_n_fb, s_invalid, s_invpre, out);
+        else emit_general<true>(lane, wbase, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_list, s_n_fb, s_invalid, s_invpre, out);
         __syncwarp();
 
         // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
