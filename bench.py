@@ -214,7 +214,8 @@ def run_ours(args):
     d_codes = torch.empty(n_kmers, dtype=torch.int64, device=dev)
     d_code_off = torch.empty(n_contigs + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(4, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real stream: the handle attaches its L2 access-policy window to it
+    torch.cuda.set_stream(stream)
 
     def step():
         f.query_device(d_bases.data_ptr(), d_off.data_ptr(), offsets, d_codes.data_ptr(), n_kmers,

@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblphash_b200.so")
+# LPHASH_B200_LIB selects a tuning variant of the same library (csrc/Makefile: `make variant`)
+LIB_PATH = os.environ.get("LPHASH_B200_LIB") or os.path.join(HERE, "liblphash_b200.so")
 
 RECORD_DTYPE = np.dtype([("itself", "<u8"), ("id", "<u8"), ("p1", "u1"), ("size", "u1")])  # mm_record_t
 

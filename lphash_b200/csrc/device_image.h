@@ -4,10 +4,9 @@
 // The image is NOT the serialized layout.  It holds the same function re-laid-out for the GPU
 // (results are bit-identical; lph_image.cpp does the transformations once, at load time):
 //   * pilots: the reference's dual<dictionary,dictionary> (pthash encoders.hpp:167-176, 268-277)
-//     is two (ranks, dict) compact-vector pairs; here both halves are merged into ONE rank array
-//     (u16 when the two dictionaries together have <= 65536 entries, else u32) indexing ONE table
-//     that already holds default_hash64(pilot, seed) (single_phf.hpp:58): one 2-byte and one 8-byte
-//     load and no second murmur per probe.
+//     is two (ranks, dict) compact-vector pairs; here every bucket directly holds
+//     default_hash64(pilot, seed) (single_phf.hpp:58): ONE 8-byte gather per probe instead of two
+//     dependent ones, and no second murmur.
 //   * free slots: pthash's Elias-Fano `free_slots` (single_phf.hpp:61-63) decoded into a plain
 //     u32 array (table_size < 2^32 because 64-bit PTHash hashes cap num_keys at 2^30,
 //     hasher.hpp:27-31).
@@ -19,7 +18,9 @@
 //     entry = flags | base; top bit: slope +1 (LEFT, MAXIMAL) else -1 (RIGHT, NONE); next bit:
 //     colliding minimizer (base unused; every k-mer goes through fallback_kmer_order).
 //     32-bit entries when every base < 2^30, else 64-bit.  One gather per super-k-mer instead of
-//     two rank lookups and up to three Elias-Fano accesses.
+//     two rank lookups and up to three Elias-Fano accesses.  The table has table_size entries,
+//     indexed by the PTHash slot BEFORE the minimal remap: a slot >= num_keys repeats the word of
+//     the position free_slots maps it to, so no free-slot lookup is needed either.
 #pragma once
 #include <stdint.h>
 
@@ -30,13 +31,11 @@ struct DevPhf {              // pthash::single_phf<*, dictionary_dictionary, tru
     uint64_t dense, sparse;  // skew_bucketer bucket counts (bucketers.hpp:10-22); all < 2^32
     // 96-bit reciprocals ceil(2^96/d) (exact a % d for 64-bit a and d < 2^32)
     uint32_t m_table[3], m_dense[3], m_sparse[3];
-    uint32_t ranks_are_u16;
-    const void* ranks;       // one entry per bucket, index into hashed_pilots
-    const uint64_t* hashed_pilots;
+    const uint64_t* pilot_hash;  // per bucket: default_hash64(pilot, seed)
     const uint32_t* free32;  // free32[i] == free_slots.access(i)
 };
 
-struct DevBuckets {          // per bucket id: kind | base (see above)
+struct DevBuckets {          // per PTHash table slot: flags | base (see above)
     const void* entries;
     uint32_t wide;           // 0: uint32_t entries (flags in bits 30-31), 1: uint64_t (bits 62-63)
     uint64_t n;

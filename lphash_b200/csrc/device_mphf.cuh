@@ -47,6 +47,30 @@ LPHB_DEV uint32_t mod_small(uint64_t a, uint32_t M0, uint32_t M1, uint32_t M2, u
     return uint32_t(q);
 }
 
+// Gathers from the image carry an L2 evict_last policy: the image (a few bytes per minimizer,
+// read at random by every SM) should stay resident in the 126 MB L2 while the base stream and the
+// codes (read/written once, evict-first) flow through it.
+LPHB_DEV uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+LPHB_DEV uint32_t ldg_keep(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+LPHB_DEV uint32_t ldg_keep(const uint16_t* p, uint64_t pol) {
+    uint16_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return v;
+}
+LPHB_DEV uint64_t ldg_keep(const uint64_t* p, uint64_t pol) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // pthash::single_phf::position, in the stages a caller may interleave across several keys.
 // ref: pthash/include/single_phf.hpp:55-65; skew_bucketer::bucket pthash/include/utils/
 // bucketers.hpp:17-22 (T = (uint64_t)(0.6*UINT64_MAX) evaluated in double = 0x9999999999999800);
@@ -61,16 +85,11 @@ LPHB_DEV uint32_t phf_bucket(DevPhf const& p, uint64_t h) {
     const uint32_t r2 = dn ? p.m_dense[2] : p.m_sparse[2];
     return mod_small(h, r0, r1, r2, d) + (dn ? 0u : uint32_t(p.dense));
 }
-LPHB_DEV uint32_t phf_pilot_rank(DevPhf const& p, uint32_t bucket) {
-    return p.ranks_are_u16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(p.ranks) + bucket))
-                           : __ldg(reinterpret_cast<const uint32_t*>(p.ranks) + bucket);
-}
 LPHB_DEV uint32_t phf_table_slot(DevPhf const& p, uint64_t h_xor_pilot) {
     return mod_small(h_xor_pilot, p.m_table[0], p.m_table[1], p.m_table[2], uint32_t(p.table_size));
 }
 LPHB_DEV uint64_t phf_position(DevPhf const& p, uint64_t h) {
-    const uint32_t rk = phf_pilot_rank(p, phf_bucket(p, h));
-    const uint32_t pos = phf_table_slot(p, h ^ __ldg(p.hashed_pilots + rk));
+    const uint32_t pos = phf_table_slot(p, h ^ __ldg(p.pilot_hash + phf_bucket(p, h)));
     if (pos < p.num_keys) return pos;
     return __ldg(p.free32 + (pos - uint32_t(p.num_keys)));  // minimal remap, single_phf.hpp:61-63
 }

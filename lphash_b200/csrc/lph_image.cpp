@@ -136,7 +136,7 @@ ImageBuilder::Bits ImageBuilder::read_bits(Cursor& c) {
 // quartet_wtree::rank_of (src/quartet_wtree.cpp:84-99) obtains from its rank directories are
 // plain running counters here.  `sp` = decoded sizes_and_positions prefix sums.
 void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits const& max_none,
-                                 std::vector<uint64_t> const& sp) {
+                                 std::vector<uint64_t> const& sp, std::vector<uint32_t> const& free_slots) {
     const uint64_t D = img_.distinct_minimizers;
     const uint64_t w = img_.w, maxblock = w * img_.n_maximal;
     const uint64_t rs = img_.right_start, ns = img_.none_sizes_start, np = img_.none_pos_start;
@@ -145,7 +145,11 @@ void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits 
         return sp[i];
     };
     img_.collision_base = S(np) + maxblock;  // partitioned_mphf.cpp:308-311
-    std::vector<uint64_t> e(D);
+    // The table is indexed by the PTHash table slot BEFORE the minimal remap: slots >= num_keys
+    // repeat the word of the key position free_slots sends them to (single_phf.hpp:61-63), so the
+    // query needs no free-slot lookup.
+    const uint64_t T = D + free_slots.size();
+    std::vector<uint64_t> e(T);
     uint64_t n0 = 0, n1 = 0;              // zeros / ones of root seen so far
     uint64_t r_left = 0, r_right = 0, r_max = 0, r_none = 0;
     uint64_t max_base = 0;
@@ -185,16 +189,20 @@ void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits 
         // bit 63: slope +1 (else -1), bit 62: colliding minimizer
         e[b] = (uint64_t(kind == 1) << 63) | (uint64_t(kind == 0) << 62) | base;
     }
-    img_.buckets.n = D;
+    for (uint64_t i = 0; i < free_slots.size(); ++i) {
+        if (free_slots[i] >= D) throw FormatError("single_phf: free slot outside [0, num_keys)");
+        e[D + i] = e[free_slots[i]];
+    }
+    img_.buckets.n = T;
     if (max_base < (1ull << 30)) {
-        std::vector<uint32_t> e32(D);
-        for (uint64_t b = 0; b < D; ++b)
+        std::vector<uint32_t> e32(T);
+        for (uint64_t b = 0; b < T; ++b)
             e32[b] = uint32_t(e[b] >> 62) << 30 | uint32_t(e[b] & 0x3FFFFFFFull);  // same two flag bits on top
         img_.buckets.wide = 0;
-        img_.buckets.entries = append(e32.data(), D, 8);
+        img_.buckets.entries = append(e32.data(), T, 8);
     } else {
         img_.buckets.wide = 1;
-        img_.buckets.entries = append(e.data(), D, 4);
+        img_.buckets.entries = append(e.data(), T, 4);
     }
 }
 
@@ -222,12 +230,13 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
     if (out.table_size == 0 || out.table_size < out.num_keys)
         throw FormatError("single_phf: bad table size");
     if (out.dense == 0 || out.sparse == 0) throw FormatError("single_phf: empty bucket class");
+    // one word per bucket: default_hash64(pilot of the bucket, seed) (single_phf.hpp:57-58), the
+    // dictionary indirection of dual<dictionary, dictionary> resolved here
     std::vector<uint64_t> hp(ndict);
     for (uint64_t i = 0; i < fd.size; ++i) hp[i] = murmur64_host(fd.get(i), out.seed);
     for (uint64_t i = 0; i < bd.size; ++i) hp[fd.size + i] = murmur64_host(bd.get(i), out.seed);
-    out.hashed_pilots = append(hp.data(), ndict, 1);
-    out.ranks_are_u16 = ndict <= 65536 ? 1u : 0u;
-    auto rank_of_bucket = [&](uint64_t b) -> uint64_t {
+    std::vector<uint64_t> per_bucket(nbuckets);
+    for (uint64_t b = 0; b < nbuckets; ++b) {
         uint64_t r;
         if (b < fr.size) {
             r = fr.get(b);
@@ -237,18 +246,9 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
             if (r >= bd.size) throw FormatError("pilot rank outside dictionary");
             r += fd.size;
         }
-        return r;
-    };
-    if (out.ranks_are_u16) {
-        std::vector<uint16_t> rk(nbuckets);
-        for (uint64_t b = 0; b < nbuckets; ++b) rk[b] = uint16_t(rank_of_bucket(b));
-        out.ranks = append(rk.data(), nbuckets, 8);
-    } else {
-        if (ndict > 0xFFFFFFFFull) throw FormatError("pilot dictionary too large");
-        std::vector<uint32_t> rk(nbuckets);
-        for (uint64_t b = 0; b < nbuckets; ++b) rk[b] = uint32_t(rank_of_bucket(b));
-        out.ranks = append(rk.data(), nbuckets, 4);
+        per_bucket[b] = hp[r];
     }
+    out.pilot_hash = append(per_bucket.data(), nbuckets, 2);
     if (out.table_size >= (1ull << 32) || out.dense >= (1ull << 32) || out.sparse >= (1ull << 32))
         throw FormatError("single_phf: table larger than 2^32 (impossible with 64-bit PTHash hashes)");
     reciprocal96(out.table_size, out.m_table);
@@ -264,6 +264,7 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
         f32[i] = uint32_t(free_vals[i]);
     }
     out.free32 = append(f32.data(), f32.size(), 4);
+    last_free_ = std::move(f32);
 }
 
 void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
@@ -285,6 +286,7 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
         throw FormatError("k/m out of range for this kmer_t");
     img_.w = img_.k - img_.m + 1;
     read_phf(c, img_.minimizer_order);
+    std::vector<uint32_t> mo_free = std::move(last_free_);
     Bits root = read_bits(c), left_right = read_bits(c), max_none = read_bits(c);
     std::vector<uint64_t> sp = read_ef(c);
     read_phf(c, img_.fallback);
@@ -296,7 +298,7 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (!(img_.right_start <= img_.none_sizes_start && img_.none_sizes_start <= img_.none_pos_start &&
           img_.none_pos_start < sp.size()))
         throw FormatError("inconsistent sizes_and_positions partition");
-    build_buckets(root, left_right, max_none, sp);
+    build_buckets(root, left_right, max_none, sp, mo_free);
     fallback_keys_ = img_.fallback.num_keys;
     file_bytes_ = n;
     arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
@@ -307,8 +309,7 @@ DevImage ImageBuilder::rebased(const void* device_base) const {
     auto* base = static_cast<const uint8_t*>(device_base);
     for (DevPhf* p : {&d.minimizer_order, &d.fallback}) {
         p->free32 = reinterpret_cast<const uint32_t*>(base + uintptr_t(p->free32));
-        p->ranks = base + uintptr_t(p->ranks);
-        p->hashed_pilots = reinterpret_cast<const uint64_t*>(base + uintptr_t(p->hashed_pilots));
+        p->pilot_hash = reinterpret_cast<const uint64_t*>(base + uintptr_t(p->pilot_hash));
     }
     d.buckets.entries = base + uintptr_t(d.buckets.entries);
     return d;

@@ -50,11 +50,12 @@ private:
     Bits read_bits(Cursor& c);
     void read_phf(Cursor& c, DevPhf& out);
     void build_buckets(Bits const& root, Bits const& left_right, Bits const& max_none,
-                       std::vector<uint64_t> const& sp);
+                       std::vector<uint64_t> const& sp, std::vector<uint32_t> const& free_slots);
 
     std::vector<uint8_t> arena_;
     DevImage img_{};
     uint64_t fallback_keys_ = 0, file_bytes_ = 0;
+    std::vector<uint32_t> last_free_;  // free slots of the PHF parsed last
 };
 
 // ceil(2^96 / d) as three 32-bit limbs (d >= 1, d < 2^32); limbs all zero for d == 1.

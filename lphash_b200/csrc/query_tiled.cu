@@ -1,32 +1,39 @@
-// Tiled streaming-query kernel (the hot path) for window widths W = k-m+1 <= 17.
+// Streaming-query kernel (the hot path) for window widths W = k-m+1 <= 17.
 //
-// The concatenated base stream is cut into tiles of TILE = 8 warps x 31 lanes x 16 k-mer starts.
-// One CTA (256 threads) per tile, five phases separated by CTA barriers:
+// The concatenated base stream is cut into WARP TILES of 992 k-mer starts (2 strips x 31 lanes x
+// 16 starts).  The grid is persistent (as many CTAs as fit the GPU); every WARP walks its own
+// sequence of tiles (tile = global warp id, + number of warps, ...) and owns all the shared memory
+// it touches, so there is no CTA barrier anywhere: a warp stalled on a probe never holds up the
+// others.  Per tile:
 //
-//  A  load+pack   one coalesced 16-byte load per thread (16 ASCII bases) -> one 32-bit word of
-//                 2-bit codes (first base in the most significant bits, the reference's m-mer /
-//                 k-mer orientation, partitioned_mphf.hpp:106-108) -> shared memory.  Non-ACGT
-//                 bytes flag their contig dirty (it is then recomputed by the exact sequential
-//                 kernel).  Warp 0 meanwhile rasterises contig seams into a
-//                 bitmask of invalid k-mer starts.
-//  B  scan        each thread owns 16 consecutive k-mer starts.  16 m-mer hashes from registers
-//                 (MurmurHash2-64, seeded); each is reduced to a 32-bit key = top 27 bits of the
-//                 hash | 5-bit thread-local position, so that ONE unsigned min picks the smaller
-//                 hash and, between equal keys, the leftmost.  The W-1 keys a thread lacks come
-//                 from lane+1 by warp shuffle (lane 31 only feeds lane 30: warps overlap by one
-//                 lane).  Sliding minimum = sparse table of 3-input minima (VIMNMX3): spans of 3,
-//                 9, then two spans cover the window.  A second pass with the position bits
-//                 complemented finds the RIGHTMOST minimum; if the two differ anywhere the 27-bit
-//                 keys tied (true repeat or truncation tie) and that thread recomputes its 16
-//                 windows from the full 64-bit hashes (out of line, rare).  Result: minimizer
-//                 offset of every k-mer + mask of positions that are some k-mer's minimizer.
-//  C  compact     minimizer positions of the warp -> dense list in shared memory (warp scan).
-//  D  probe       one lane per distinct minimizer position: m-mer -> PTHash -> bucket table
-//                 (device_mphf.cuh) -> {B, ns} with  code(k-mer at q) = B + ns * q.
-//  E  emit        position-parallel: lane l handles k-mers l, l+32, ...: two byte loads find the
-//                 entry, one IMAD.WIDE makes the code, 8-byte stores are fully coalesced.
-//                 K-mers of colliding minimizers are queued and resolved through
-//                 fallback_kmer_order (partitioned_mphf.cpp:308-313).
+//  A  stage+pack   the tile's ASCII bytes (1040 B incl. k-1 bases of overlap) arrive in shared
+//                  memory by ONE TMA bulk copy (cp.async.bulk -> mbarrier), issued one tile ahead
+//                  (double buffer), so the global-load latency is never exposed.  Each lane then
+//                  packs 16-byte words to 32-bit words of 2-bit codes (first base in the most
+//                  significant bits, the reference's m-mer / k-mer orientation,
+//                  partitioned_mphf.hpp:106-108).  Non-ACGT bytes flag their contig dirty (it is
+//                  then recomputed by the exact sequential kernel).  Contig seams
+//                  are rasterised into a bitmask of k-mer starts that produce no code (skipped
+//                  entirely when the tile lies inside one contig, which the set-up kernel records).
+//  B  scan         each thread owns 16 consecutive k-mer starts.  16 m-mer hashes from registers
+//                  (MurmurHash2-64, seeded); each is reduced to a 32-bit key = top 27 bits of the
+//                  hash | 5-bit thread-local position, so that ONE unsigned min picks the smaller
+//                  hash and, between equal keys, the leftmost.  The W-1 keys a thread lacks come
+//                  from lane+1 by warp shuffle (lane 31 only feeds lane 30).  Sliding minimum =
+//                  sparse table of 3-input minima (VIMNMX3): spans of 3, 9, then two spans cover
+//                  the window.  A second pass with the position bits complemented finds the
+//                  RIGHTMOST minimum; if the two differ anywhere the 27-bit keys tied (true repeat
+//                  or truncation tie) and that thread recomputes its 16 windows from the full
+//                  64-bit hashes (out of line, rare).  Result: minimizer offset of every k-mer +
+//                  mask of positions that are some k-mer's minimizer.
+//  C  compact      minimizer positions of the tile -> dense list in shared memory (warp scan).
+//  D  probe        one lane per distinct minimizer position, kProbes in flight per lane:
+//                  m-mer -> PTHash (one 8-byte gather) -> bucket table (one 4/8-byte gather)
+//                  (device_mphf.cuh) -> {B, ns} with  code(k-mer at q) = B + ns * q.
+//  E  emit         position-parallel: lane l handles k-mers l, l+32, ...: two byte loads find the
+//                  entry, one multiply-add makes the code, 8-byte stores are fully coalesced.
+//                  K-mers of colliding minimizers are flagged and resolved through
+//                  fallback_kmer_order (partitioned_mphf.cpp:308-313).
 //
 // Every k-mer's code is a pure function of its own k bases, so tiles only share
 // k-1 bases of read overlap and nothing else.
@@ -40,34 +47,60 @@ namespace lphb {
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 4;                      // warps per CTA (independent of each other)
 constexpr int kThreads = kWarps * 32;
 constexpr int kS = 16;                         // k-mer starts per thread = bases per packed word
 constexpr int kLanes = 31;                     // producing lanes per warp (lane 31 only feeds lane 30)
 constexpr int kStrip = kLanes * kS;            // 496 k-mer starts per warp pass
-constexpr int kStrips = 2;                     // passes per warp
-constexpr int kWarpKmers = kStrips * kStrip;   // 992 k-mer starts per warp
-constexpr int kTile = kWarps * kWarpKmers;     // 3968 k-mer starts per tile (CTA)
-constexpr int kMaskWords = kTile / 32;         // 124
-constexpr int kMaskSlots = kMaskWords + 1;
-constexpr int kWarpSlots = kWarpKmers + 32;    // positions a minimizer of the warp's k-mers can sit at
-constexpr int kWarpMaskWords = kWarpSlots / 32;  // 32: one word per lane
-constexpr int kProbes = 6;                     // probes a lane keeps in flight
-constexpr int kCap = 32 * kProbes;             // probe results held at once per warp (index fits a byte)
-struct Entry {                                 // code of the k-mer at warp-local q = B + ns * q (mod 2^64)
+constexpr int kStrips = 2;                     // passes per tile
+constexpr int kTile = kStrips * kStrip;        // 992 k-mer starts per (warp) tile
+constexpr int kMaskWords = kTile / 32;         // 31 words of the invalid-start mask
+constexpr int kSlots = kTile + 32;             // positions a minimizer of the tile's k-mers can sit at
+constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
+#ifndef LPHB_PROBES
+#define LPHB_PROBES 3
+#endif
+#ifndef LPHB_MINB
+#define LPHB_MINB 6
+#endif
+constexpr int kProbes = LPHB_PROBES;           // probes a lane keeps in flight
+constexpr int kGroups = 6;                     // 32-probe groups whose results a warp holds at once
+constexpr int kCap = 32 * kGroups;             // = 192 (the list index fits a byte)
+struct Entry {                                 // code of the k-mer at tile-local q = B + ns * q (mod 2^64)
     uint32_t lo;                               // low word of B (the high word lives in s_hi)
     int32_t ns;                                // -1: LEFT/MAXIMAL, +1: RIGHT/NONE, 0: colliding minimizer
 };
-constexpr int kWarpBytes = kCap * (8 + 4) + kWarpSlots * (1 + 1 + 2) + (kWarpMaskWords + 4 + 16) * 4;
-constexpr int kPackedSlots = 256;
-constexpr int kSmemBytes = kWarps * kWarpBytes + kPackedSlots * 4 + kMaskSlots * (4 + 2) + 16;
-static_assert(kWarpMaskWords == 32 && kWarpBytes % 16 == 0, "per-warp layout");
+constexpr int kPackedSlots = 68;               // packed words per tile: 62 + overlap + read-ahead of mmer_at
+constexpr int kRawBytes = 1088;                // ASCII bytes of one tile incl. overlap (<= 68 words), one TMA copy
+// per-warp shared memory (bytes)
+constexpr int kOffEnt = 0;                               // Entry[kCap]
+constexpr int kOffHi = kOffEnt + kCap * 8;               // u32[kCap]
+constexpr int kOffList = kOffHi + kCap * 4;              // u16[kCap]
+constexpr int kOffPos = kOffList + kCap * 2;             // u8[kSlots]
+constexpr int kOffRef = kOffPos + kSlots;                // u8[kSlots]
+constexpr int kOffMin = kOffRef + kSlots;                // u32[32] minimizer-position mask
+constexpr int kOffFb = kOffMin + 128;                    // u32[32] fallback k-mers
+constexpr int kOffInv = kOffFb + 128;                    // u32[32] invalid starts
+constexpr int kOffWpre = kOffInv + 128;                  // u16[32] marked positions before mask word
+constexpr int kOffInvPre = kOffWpre + 64;                // u16[32] invalid starts before mask word
+constexpr int kOffPacked = kOffInvPre + 64;              // u32[kPackedSlots]
+constexpr int kOffRaw = (kOffPacked + kPackedSlots * 4 + 15) / 16 * 16;  // 2 x kRawBytes (TMA destinations)
+constexpr int kOffBar = kOffRaw + 2 * kRawBytes;         // 2 mbarriers
+constexpr int kWarpBytes = kOffBar + 16;
+constexpr int kSmemBytes = kWarps * kWarpBytes;
+static_assert(kSlotWords == 32 && kWarpBytes % 16 == 0 && kOffRaw % 16 == 0 && kRawBytes % 16 == 0, "per-warp layout");
+
+// what the set-up kernel records per tile
+struct __align__(16) TileRec {
+    uint64_t out;      // number of valid k-mer starts (codes) before the tile
+    uint32_t c0;       // contig containing the tile's first in-range position
+    uint32_t clean;    // 1: every start of the tile yields a code (one contig covers tile + k-1 bases)
+};
 
 struct TileArgs {
     const char* abase;          // 16-byte aligned; stream position pos0 lives here
     int64_t pos0;               // stream position of abase (may be < first_base by < 16)
-    const uint32_t* tile_c0;    // per tile: contig containing the tile's first in-range position
-    const uint64_t* tile_out;   // per tile: number of valid k-mer starts before it
+    const TileRec* recs;        // per tile
     uint32_t n_tiles;
 };
 
@@ -109,16 +142,46 @@ static __device__ __noinline__ uint64_t fallback_code(DevImage const& f, uint64_
     return f.collision_base + fallback_order(f, klo, khi);
 }
 
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// the base stream is read once: evict-first in L2, so that it does not displace the image
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_stream_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 template <int K, int M>
 struct Cfg {
     static constexpr int W = K - M + 1;
     static constexpr int NW = (kS + K - 1 + 15) / 16;        // packed words a thread reads
     static constexpr int NH = kS + W - 1;                    // m-mers under a thread's 16 windows
-    static constexpr int TileWords = kTile / 16 + NW;        // words staged per tile
+    static constexpr int TileWords = kTile / 16 + NW;        // 16-byte words staged per tile
     static_assert(W >= 1 && W <= 17, "tiled kernel: window must fit one shuffle hop");
     static_assert(NH <= 32, "thread-local minimizer positions must fit the 5-bit key field");
     static_assert(M <= 31 && K <= 63, "k, m out of range");
-    static_assert(TileWords <= kPackedSlots, "packed tile must fit its shared-memory array");
+    static_assert(TileWords + 2 <= kPackedSlots && TileWords * 16 <= kRawBytes, "tile must fit its buffers");
 };
 
 // a * 0xc6a4a7935bd1e995 mod 2^64 in three multiply-adds (IMAD.WIDE + 2 IMAD, all on the FMA pipe)
@@ -212,20 +275,20 @@ static __device__ __noinline__ uint32_t exact_strip(const uint32_t* s_packed, in
     return marks;
 }
 
-// Codes of the k-mers of a warp, position-parallel: lane l handles k-mers l, l+32, ...; two byte
+// Codes of the k-mers of a tile, position-parallel: lane l handles k-mers l, l+32, ...; two byte
 // loads find the entry of the k-mer's minimizer, code = B + ns * q, coalesced 8-byte stores.
 //
-// Plain form, for a warp whose 992 starts all yield a code, whose entries share the high word
+// Plain form, for a tile whose 992 starts all yield a code, whose entries share the high word
 // `hi` of B and cannot carry out of the low word (1024 <= lo < 2^32 - 1024), with no colliding
 // minimizer and a single chunk: one 32-bit multiply-add per code.
 __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
-                                           const Entry* s_ent, uint32_t hi, uint64_t* out_warp) {
+                                           const Entry* s_ent, uint32_t hi, uint64_t* out_tile) {
     const uint8_t* pos_l = s_pos + lane;
     const uint8_t* ref_l = s_ref + (lane & 16);
-    uint2* o = reinterpret_cast<uint2*>(out_warp + lane);
+    uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
 #pragma unroll 8
-    for (int r = 0; r < kWarpKmers / 32; ++r) {
-        const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) warp-local position of the minimizer
+    for (int r = 0; r < kTile / 32; ++r) {
+        const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) tile-local position of the minimizer
         const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
         uint32_t lo;
         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
@@ -235,27 +298,25 @@ __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const
 
 // General form.  Per group of 32 starts the (warp-uniform) word of the invalid-start mask tells
 // whether starts without a code (contig seams) must be skipped and the output index compacted;
-// k-mers of colliding minimizers are queued in s_list; kChunked (more than kCap minimizers):
+// k-mers of colliding minimizers are flagged in s_fbmask; kChunked (more than kCap minimizers):
 // entries outside [i0, i1) are left to their own chunk.
 template <bool kChunked>
-__device__ __forceinline__ void emit_general(int lane, int wbase, uint32_t i0, uint32_t i1,
+__device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
                                              const uint8_t* s_pos, const uint8_t* s_ref,
                                              const uint32_t* s_minmask, const uint16_t* s_wpre,
                                              const Entry* s_ent, const uint32_t* s_hi,
-                                             uint16_t* s_list, uint32_t* s_n_fb,
+                                             uint32_t* s_fbmask,
                                              const uint32_t* s_invalid, const uint16_t* s_invpre,
                                              uint64_t* out) {
     const int lane16 = lane & 16;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t* inv = s_invalid + (wbase >> 5);  // wbase is a multiple of 32
-    const uint16_t* pre = s_invpre + (wbase >> 5);
-    uint64_t* out_l = out + wbase + lane;
+    uint64_t* out_l = out + lane;
 #pragma unroll 2
-    for (int r = 0; r < kWarpKmers / 32; ++r) {
+    for (int r = 0; r < kTile / 32; ++r) {
         const int q = lane + r * 32;
-        const uint32_t mw = inv[r];  // uniform in the warp
+        const uint32_t mw = s_invalid[r];  // uniform in the warp
         if ((mw >> lane) & 1u) continue;
-        const int mp = int(s_pos[q]) + lane16 + r * 32;  // warp-local position of q's minimizer
+        const int mp = int(s_pos[q]) + lane16 + r * 32;  // tile-local position of q's minimizer
         uint32_t idx;
         if (kChunked) {  // global list index of position mp: rank among the marked positions
             idx = s_wpre[mp >> 5] + __popc(s_minmask[mp >> 5] & ((1u << (mp & 31)) - 1u));
@@ -266,343 +327,387 @@ __device__ __forceinline__ void emit_general(int lane, int wbase, uint32_t i0, u
         }
         const Entry e = s_ent[idx];
         if (e.ns == 0) {  // colliding minimizer: needs the k-mer itself
-            s_list[atomicAdd(s_n_fb, 1u)] = uint16_t(q);
+            atomicOr(&s_fbmask[r], 1u << lane);
             continue;
         }
         const uint64_t B = (uint64_t(s_hi[idx]) << 32) | e.lo;
         const uint64_t code = B + uint64_t(int64_t(e.ns) * int64_t(q));
-        __stcs(out_l + (r * 32 - int(pre[r]) - __popc(mw & lt)), code);
+        __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), code);
     }
 }
 
 template <int K, int M>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, LPHB_MINB)
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
     constexpr int W = C::W, NW = C::NW, NH = C::NH;
 
-    // dynamic shared memory: one private region per warp (warp-local coordinates) + tile-wide
-    // packed bases and invalid-start bitmask
+    // dynamic shared memory: one private region per warp, tile-local coordinates
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem_raw + warp * kWarpBytes;
-    Entry* s_ent = reinterpret_cast<Entry*>(mine);                          // per probe (list index)
-    uint32_t* s_hi = reinterpret_cast<uint32_t*>(s_ent + kCap);            // per probe: high word of B
-    uint8_t* s_pos = reinterpret_cast<uint8_t*>(s_hi + kCap);              // per k-mer: thread-local minimizer position
-    uint8_t* s_ref = s_pos + kWarpSlots;                                   // per position: chunk-local list index
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_ref + kWarpSlots);    // minimizer positions (chunk); later colliding k-mers
-    uint32_t* s_minmask = reinterpret_cast<uint32_t*>(s_list + kWarpSlots);  // bit b: position b is some k-mer's minimizer
-    uint32_t* s_n_fb = s_minmask + kWarpMaskWords;                         // colliding k-mers queued
-    uint16_t* s_wpre = reinterpret_cast<uint16_t*>(s_n_fb + 4);            // per mask word: marked positions before it
-    uint32_t* s_packed = reinterpret_cast<uint32_t*>(smem_raw + kWarps * kWarpBytes);  // 2-bit bases (tile)
-    uint32_t* s_invalid = s_packed + kPackedSlots;     // bit q: k-mer start q produces no code (tile)
-    uint16_t* s_invpre = reinterpret_cast<uint16_t*>(s_invalid + kMaskSlots);  // invalid starts before word
+    Entry* s_ent = reinterpret_cast<Entry*>(mine + kOffEnt);          // per probe (list index)
+    uint32_t* s_hi = reinterpret_cast<uint32_t*>(mine + kOffHi);      // per probe: high word of B
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(mine + kOffList);  // minimizer positions of the chunk
+    uint8_t* s_pos = mine + kOffPos;                                  // per k-mer: thread-local minimizer position
+    uint8_t* s_ref = mine + kOffRef;                                  // per position: chunk-local list index
+    uint32_t* s_minmask = reinterpret_cast<uint32_t*>(mine + kOffMin);  // bit p: position p is some k-mer's minimizer
+    uint32_t* s_fbmask = reinterpret_cast<uint32_t*>(mine + kOffFb);    // bit q: k-mer q needs fallback_kmer_order
+    uint32_t* s_invalid = reinterpret_cast<uint32_t*>(mine + kOffInv);  // bit q: k-mer start q produces no code
+    uint16_t* s_wpre = reinterpret_cast<uint16_t*>(mine + kOffWpre);    // marked positions before mask word
+    uint16_t* s_invpre = reinterpret_cast<uint16_t*>(mine + kOffInvPre);  // invalid starts before mask word
+    uint32_t* s_packed = reinterpret_cast<uint32_t*>(mine + kOffPacked);  // 2-bit bases of the tile
+    unsigned char* s_rawbuf = mine + kOffRaw;                         // 2 x raw ASCII (TMA destinations)
+    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(mine + kOffBar);
 
-    const uint32_t tile = blockIdx.x;
-    const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
     const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
-
-    // ---------------------------------------------------------------- A: load + pack ------------
-    if (tid < kMaskSlots) s_invalid[tid] = 0;
-    s_minmask[lane] = 0;
-    if (lane == 0) *s_n_fb = 0;
-    for (int t = tid; t < kPackedSlots; t += kThreads) {
-        int64_t wpos = T0 + int64_t(t) * 16;
-        uint32_t word = 0;
-        if (t < C::TileWords && wpos + 16 > first && wpos < end) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.abase + (wpos - a.pos0)));
-            uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
-            word = (pack4(y0) << 24) | (pack4(y1) << 16) | (pack4(y2) << 8) | pack4(y3);
-            uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
-            if (bad) mark_dirty(b, v, wpos);  // rare
+    const uint32_t n_warps = gridDim.x * kWarps;
+    uint32_t tile = blockIdx.x * kWarps + warp;
+    // bytes of tile t that exist (whole 16-byte words up to the one holding the last base)
+    auto tile_bytes = [&](uint32_t t) -> uint32_t {
+        const int64_t t0 = a.pos0 + int64_t(t) * kTile;
+        int64_t words = (end - t0 + 15) >> 4;
+        if (words > C::TileWords) words = C::TileWords;
+        return uint32_t(words) * 16u;
+    };
+    const uint64_t stream_pol = l2_stream_policy();
+    if (lane == 0) {
+        mbar_init(&s_mbar[0], 1);
+        mbar_init(&s_mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < a.n_tiles) {  // first tile of this warp
+            const uint32_t nb = tile_bytes(tile);
+            mbar_expect_tx(&s_mbar[0], nb);
+            tma_load_1d(s_rawbuf, a.abase + int64_t(tile) * kTile, nb, &s_mbar[0], stream_pol);
         }
-        s_packed[t] = word;
     }
-    __syncthreads();  // zeroed masks + packed words visible
+    __syncwarp();
+    TileRec rec{};
+    if (tile < a.n_tiles) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.recs + tile));
+        rec.out = (uint64_t(v.y) << 32) | v.x;
+        rec.c0 = v.z;
+        rec.clean = v.w;
+    }
+    const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
+    uint32_t keymask;  // ~31 held in a register so that (hash & ~31) | position is one LOP3
+    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(keymask));
 
-    // warp 0: rasterise the k-mer starts that produce no code (contig seams, short contigs,
-    // positions outside [first, end)) into s_invalid
-    if (warp == 0) {
-        const int64_t tile_end = T0 + kTile;
-        if (T0 < first) {  // head padding of the first tile (< 16 positions)
-            int n = int(first - T0);
-            if (lane == 0) atomicOr(&s_invalid[0], (1u << n) - 1u);
+    uint32_t iter = 0;
+#pragma unroll 1
+    for (; tile < a.n_tiles; tile += n_warps, ++iter) {
+        const uint32_t buf = iter & 1u;
+        const unsigned char* s_raw = s_rawbuf + buf * kRawBytes;
+        const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
+        const TileRec cur = rec;
+
+        // ------------------------------------------------------------ A: stage + pack ------------
+        // prefetch this warp's next tile into the other raw buffer (all lanes finished reading it
+        // one iteration ago) and its set-up record into registers; then wait for this tile's bytes
+        const uint32_t next = tile + n_warps;
+        if (next < a.n_tiles) {
+            if (lane == 0) {
+                const uint32_t nb = tile_bytes(next);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s_mbar[buf ^ 1u], nb);
+                tma_load_1d(s_rawbuf + (buf ^ 1u) * kRawBytes, a.abase + int64_t(next) * kTile, nb,
+                            &s_mbar[buf ^ 1u], stream_pol);
+            }
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.recs + next));
+            rec.out = (uint64_t(v.y) << 32) | v.x;
+            rec.c0 = v.z;
+            rec.clean = v.w;
         }
-        uint64_t c = a.tile_c0[tile];
-        for (;; c += 32) {
-            uint64_t cc = c + lane;
-            bool live = cc < b.n_contigs;
-            int64_t s = live ? int64_t(__ldg(b.offsets + cc)) : end;
-            int64_t e = live ? int64_t(__ldg(b.offsets + cc + 1)) : end;
-            if (live && s < tile_end) {
-                // starts in [max(e-K+1, s), e) have fewer than K bases left in their contig
-                int64_t lo = e - (K - 1) > s ? e - (K - 1) : s;
-                int64_t hi = e;
-                if (lo < T0) lo = T0;
-                if (hi > tile_end) hi = tile_end;
-                for (int64_t q = lo; q < hi;) {
-                    int ql = int(q - T0);
-                    int wbit = ql & 31;
-                    int n = int(hi - q) < 32 - wbit ? int(hi - q) : 32 - wbit;
-                    uint32_t bits = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << wbit;
-                    atomicOr(&s_invalid[ql >> 5], bits);
-                    q += n;
+        s_minmask[lane] = 0;
+        s_fbmask[lane] = 0;
+        s_invalid[lane] = 0;
+        mbar_wait(&s_mbar[buf], (iter >> 1) & 1u);
+        const int n_words = int(tile_bytes(tile) >> 4);
+#pragma unroll
+        for (int t = lane; t < kPackedSlots; t += 32) {
+            uint32_t word = 0;
+            if (t < n_words) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_raw + t * 16);
+                uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
+                word = (pack4(y0) << 24) | (pack4(y1) << 16) | (pack4(y2) << 8) | pack4(y3);
+                uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
+                if (bad) mark_dirty(b, v, T0 + int64_t(t) * 16);  // rare
+            }
+            s_packed[t] = word;
+        }
+        __syncwarp();
+
+        // k-mer starts that produce no code (contig seams, short contigs, positions outside
+        // [first, end)) -> s_invalid; nothing to do when one contig covers the tile and k-1 more bases
+        const bool tile_clean = cur.clean != 0;
+        if (!tile_clean) {
+            const int64_t tile_end = T0 + kTile;
+            if (T0 < first) {  // head padding of the first tile (< 16 positions)
+                int n = int(first - T0);
+                if (lane == 0) atomicOr(&s_invalid[0], (1u << n) - 1u);
+            }
+            uint64_t c = cur.c0;
+            for (;; c += 32) {
+                uint64_t cc = c + lane;
+                bool live = cc < b.n_contigs;
+                int64_t s = live ? int64_t(__ldg(b.offsets + cc)) : end;
+                int64_t e = live ? int64_t(__ldg(b.offsets + cc + 1)) : end;
+                if (live && s < tile_end) {
+                    // starts in [max(e-K+1, s), e) have fewer than K bases left in their contig
+                    int64_t lo = e - (K - 1) > s ? e - (K - 1) : s;
+                    int64_t hi = e;
+                    if (lo < T0) lo = T0;
+                    if (hi > tile_end) hi = tile_end;
+                    for (int64_t q = lo; q < hi;) {
+                        int ql = int(q - T0);
+                        int wbit = ql & 31;
+                        int n = int(hi - q) < 32 - wbit ? int(hi - q) : 32 - wbit;
+                        uint32_t bits = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << wbit;
+                        atomicOr(&s_invalid[ql >> 5], bits);
+                        q += n;
+                    }
+                }
+                // go on while the contig after lane 31's also starts inside the tile
+                if (!__any_sync(0xFFFFFFFFu, lane == 31 && live && e < tile_end)) break;
+            }
+            if (end < tile_end) {  // past the last base of the batch
+                int lo = end > T0 ? int(end - T0) : 0;
+                if (lane >= (lo >> 5) && lane < kMaskWords) {
+                    uint32_t bits = 0xFFFFFFFFu;
+                    if (lane == (lo >> 5)) bits <<= (lo & 31);
+                    atomicOr(&s_invalid[lane], bits);
                 }
             }
-            // go on while the contig after lane 31's also starts inside the tile
-            if (!__any_sync(0xFFFFFFFFu, lane == 31 && live && e < tile_end)) break;
+            __syncwarp();
         }
-        if (end < tile_end) {  // past the last base of the batch
-            int lo = end > T0 ? int(end - T0) : 0;
-            for (int wd = (lo >> 5) + lane; wd < kMaskWords; wd += 32) {
-                uint32_t bits = 0xFFFFFFFFu;
-                if (wd == (lo >> 5)) bits <<= (lo & 31);
-                atomicOr(&s_invalid[wd], bits);
+        // exclusive prefix of invalid counts per mask word (one word per lane)
+        bool tile_has_invalid = false;
+        {
+            const uint32_t mw = tile_clean ? 0u : s_invalid[lane];
+            tile_has_invalid = __any_sync(0xFFFFFFFFu, mw != 0 && lane < kMaskWords);
+            uint32_t cnt = __popc(mw), inc = cnt;
+            if (tile_has_invalid) {
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+            }
+            s_invpre[lane] = uint16_t(inc - cnt);
+        }
+
+        // ------------------------------------------------------------ B: per-thread scan --------
+#pragma unroll 1
+        for (int strip = 0; strip < kStrips; ++strip) {
+            const int lseg = strip * kStrip + lane * kS;  // tile-local position of this thread's first k-mer
+            uint32_t wds[NW];
+#pragma unroll
+            for (int j = 0; j < NW; ++j) wds[j] = s_packed[(lseg >> 4) + j];
+
+            // keys: top 27 bits of the m-mer's hash | thread-local position (own: 0..15, the W-1
+            // received from lane+1: 16..)
+            uint32_t key[NH];
+#pragma unroll
+            for (int j = 0; j < kS; ++j) {
+                uint32_t v_lo, v_hi;
+                if constexpr (M <= 16) {
+                    v_lo = M == 16 ? win16<NW>(wds, j) : win16<NW>(wds, j) >> (32 - 2 * M);
+                    v_hi = 0;
+                } else {
+                    v_lo = win16<NW>(wds, j + M - 16);
+                    v_hi = win16<NW>(wds, j) >> (64 - 2 * M);
+                }
+                // MurmurHash2-64 (device_mphf.cuh: murmur64) up to its last multiply: the final
+                // h ^= h >> 47 cannot change the top 32 bits
+                uint64_t x = M <= 16 ? uint64_t(v_lo) * kMurmurM : mul_murmur(v_lo, v_hi);
+                x ^= x >> 47;
+                x = mul_murmur(x);
+                uint64_t h = mul_murmur(h0 ^ x);
+                h ^= h >> 47;
+                h = mul_murmur(h);
+                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
+            }
+#pragma unroll
+            for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
+
+            uint32_t mn[kS];
+            window_min<W, NH>(key, mn);
+            // same windows with the position bits complemented: the minimum is now the RIGHTMOST one
+            // among equal 27-bit keys; both agree on every window <=> no two candidates tied
+            uint32_t agree = 31u;
+            {
+                uint32_t rkey[NH], rmn[kS];
+#pragma unroll
+                for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ 31u;
+                window_min<W, NH>(rkey, rmn);
+#pragma unroll
+                for (int i = 0; i < kS; ++i) agree &= mn[i] ^ rmn[i];
+            }
+            if (lane < kLanes) {  // lane 31 only feeds keys to lane 30
+                uint32_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
+                if (agree == 31u) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int i = 0; i < kS; ++i) marks |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        uint32_t t0 = __byte_perm(mn[4 * g4], mn[4 * g4 + 1], 0x0040);
+                        uint32_t t1 = __byte_perm(mn[4 * g4 + 2], mn[4 * g4 + 3], 0x0040);
+                        pk[g4] = __byte_perm(t0, t1, 0x5410) & 0x1F1F1F1Fu;
+                    }
+                    *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                } else {
+                    marks = exact_strip<K, M>(s_packed, lseg, f.mm_seed, s_pos + lseg);
+                }
+                // lseg is a multiple of 16: the 32 local positions straddle at most two mask words
+                const int sh = lseg & 16;
+                atomicOr(&s_minmask[lseg >> 5], marks << sh);
+                if (sh && (marks >> 16)) atomicOr(&s_minmask[(lseg >> 5) + 1], marks >> 16);
             }
         }
         __syncwarp();
-        // exclusive prefix of invalid counts per mask word (124 words: 4 per lane)
-        uint32_t cnt[4], sum = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int wd = lane * 4 + j;
-            cnt[j] = wd < kMaskWords ? __popc(s_invalid[wd]) : 0;
-            sum += cnt[j];
-        }
-        uint32_t inc = sum;
+
+        // ------------------------------------------------------------ C: rank the minimizers ----
+        // lane l owns mask word l: list index of every marked position
+        const uint32_t my_word = s_minmask[lane];
+        const uint32_t n_mine = __popc(my_word);
+        uint32_t inc = n_mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= o) inc += v;
         }
-        uint32_t run = inc - sum;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int wd = lane * 4 + j;
-            if (wd < kMaskSlots) s_invpre[wd] = uint16_t(run);
-            run += cnt[j];
-        }
-    }
-    __syncthreads();  // invalid-start mask ready; from here on every warp runs on its own
+        const uint32_t n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t my_first = inc - n_mine;
+        s_wpre[lane] = uint16_t(my_first);
 
-    // ---------------------------------------------------------------- B: per-thread scan --------
-    const int wbase = warp * kWarpKmers;  // tile-local position of this warp's first k-mer
-    const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
-    uint32_t keymask;  // ~31 held in a register so that (hash & ~31) | position is one LOP3
-    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(keymask));
-#pragma unroll 1
-    for (int strip = 0; strip < kStrips; ++strip) {
-        const int lseg = strip * kStrip + lane * kS;  // warp-local position of this thread's first k-mer
-        uint32_t wds[NW];
-#pragma unroll
-        for (int j = 0; j < NW; ++j) wds[j] = s_packed[((wbase + lseg) >> 4) + j];
+        uint64_t* out = b.codes + cur.out;
+        const bool chunked = n_min > kCap;
 
-        // keys: top 27 bits of the m-mer's hash | thread-local position (own: 0..15, the W-1
-        // received from lane+1: 16..)
-        uint32_t key[NH];
-#pragma unroll
-        for (int j = 0; j < kS; ++j) {
-            uint32_t v_lo, v_hi;
-            if constexpr (M <= 16) {
-                v_lo = M == 16 ? win16<NW>(wds, j) : win16<NW>(wds, j) >> (32 - 2 * M);
-                v_hi = 0;
-            } else {
-                v_lo = win16<NW>(wds, j + M - 16);
-                v_hi = win16<NW>(wds, j) >> (64 - 2 * M);
-            }
-            // MurmurHash2-64 (device_mphf.cuh: murmur64) up to its last multiply: the final
-            // h ^= h >> 47 cannot change the top 32 bits
-            uint64_t x = M <= 16 ? uint64_t(v_lo) * kMurmurM : mul_murmur(v_lo, v_hi);
-            x ^= x >> 47;
-            x = mul_murmur(x);
-            uint64_t h = mul_murmur(h0 ^ x);
-            h ^= h >> 47;
-            h = mul_murmur(h);
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
-        }
-#pragma unroll
-        for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
-
-        uint32_t mn[kS];
-        window_min<W, NH>(key, mn);
-        // same windows with the position bits complemented: the minimum is now the RIGHTMOST one
-        // among equal 27-bit keys; both agree on every window <=> no two candidates tied
-        uint32_t agree = 31u;
-        {
-            uint32_t rkey[NH], rmn[kS];
-#pragma unroll
-            for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ 31u;
-            window_min<W, NH>(rkey, rmn);
-#pragma unroll
-            for (int i = 0; i < kS; ++i) agree &= mn[i] ^ rmn[i];
-        }
-        if (lane < kLanes) {  // lane 31 only feeds keys to lane 30
-            uint32_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
-            if (agree == 31u) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < kS; ++i) marks |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    uint32_t t0 = __byte_perm(mn[4 * g4], mn[4 * g4 + 1], 0x0040);
-                    uint32_t t1 = __byte_perm(mn[4 * g4 + 2], mn[4 * g4 + 3], 0x0040);
-                    pk[g4] = __byte_perm(t0, t1, 0x5410) & 0x1F1F1F1Fu;
+        // ------------------------------------------------------------ D + E ----------------------
+        for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
+            const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
+            {
+                uint32_t word = my_word, idx = my_first;
+                while (word) {
+                    int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    if (idx >= i0 && idx < i1) s_list[idx - i0] = uint16_t(lane * 32 + bit);
+                    ++idx;
                 }
-                *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            } else {
-                marks = exact_strip<K, M>(s_packed, wbase + lseg, f.mm_seed, s_pos + lseg);
             }
-            // lseg is a multiple of 16: the 32 local positions straddle at most two mask words
-            const int sh = lseg & 16;
-            atomicOr(&s_minmask[lseg >> 5], marks << sh);
-            if (sh && (marks >> 16)) atomicOr(&s_minmask[(lseg >> 5) + 1], marks >> 16);
-        }
-    }
-    __syncwarp();
-
-    // ---------------------------------------------------------------- C: rank the minimizers ----
-    // lane l owns mask word l: list index of every marked position
-    uint32_t my_word = s_minmask[lane];
-    uint32_t n_mine = __popc(my_word);
-    uint32_t inc = n_mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    const uint32_t n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
-    const uint32_t my_first = inc - n_mine;
-    s_wpre[lane] = uint16_t(my_first);
-
-    uint64_t* out = b.codes + a.tile_out[tile];
-    const bool chunked = n_min > kCap;
-    // does any start of this warp's range yield no code?  (31 mask words, one per lane)
-    const bool warp_has_invalid = __any_sync(0xFFFFFFFFu, lane < kWarpKmers / 32 && s_invalid[(wbase >> 5) + lane] != 0);
-
-    // ---------------------------------------------------------------- D + E ----------------------
-    for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
-        const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
-        {
-            uint32_t word = my_word, idx = my_first;
-            while (word) {
-                int bit = __ffs(word) - 1;
-                word &= word - 1;
-                if (idx >= i0 && idx < i1) s_list[idx - i0] = uint16_t(lane * 32 + bit);
-                ++idx;
-            }
-        }
-        __syncwarp();
-        // kProbes probes per lane in flight: the dependent gathers (pilot rank -> hashed pilot ->
-        // [free slot] -> bucket word) of different probes overlap instead of queueing up
-        bool special = false, have = false;
-        uint32_t hi0 = 0;
-        {
+            __syncwarp();
+            // kProbes probes per lane in flight: the dependent gathers (hashed pilot -> bucket word)
+            // of different probes overlap instead of queueing up
+            bool special = false, have = false;
+            uint32_t hi0 = 0;
             const DevPhf& P = f.minimizer_order;
-            const uint32_t nu = (i1 - i0 + 31) >> 5;  // 32-probe groups in this chunk (uniform)
-            int bp[kProbes];
-            uint64_t h[kProbes];
-            uint32_t slot[kProbes];
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u) {
-                if (u < nu) {
-                    const uint32_t li = lane + 32 * u;
-                    bp[u] = s_list[li < i1 - i0 ? li : 0];  // dead lanes redo entry 0 (harmless)
-                    h[u] = murmur64(mmer_at<M>(s_packed, wbase + bp[u]), P.seed);
-                    slot[u] = phf_bucket(P, h[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u)
-                if (u < nu) slot[u] = phf_pilot_rank(P, slot[u]);
-            uint64_t hp[kProbes];
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u)
-                if (u < nu) hp[u] = __ldg(P.hashed_pilots + slot[u]);
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u)
-                if (u < nu) slot[u] = phf_table_slot(P, h[u] ^ hp[u]);
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u)
-                if (u < nu && slot[u] >= uint32_t(P.num_keys)) slot[u] = __ldg(P.free32 + (slot[u] - uint32_t(P.num_keys)));
-            // bucket word -> {B, ns}: hval = base + slope * (bp - q) = (base + slope * bp) + (-slope) * q
-            uint64_t word[kProbes];
-#pragma unroll
-            for (int u = 0; u < kProbes; ++u) {
-                if (u < nu) {
-                    if (f.buckets.wide) word[u] = __ldg(reinterpret_cast<const uint64_t*>(f.buckets.entries) + slot[u]);
-                    else word[u] = __ldg(reinterpret_cast<const uint32_t*>(f.buckets.entries) + slot[u]);
-                }
-            }
+            const uint64_t keep = l2_keep_policy();
+            const uint32_t n_chunk = i1 - i0;
+            const uint32_t nu = (n_chunk + 31) >> 5;  // 32-probe groups in this chunk (uniform)
             const int fsh = f.buckets.wide ? 62 : 30;
             const uint64_t bmask = (uint64_t(1) << fsh) - 1;
+#pragma unroll 1
+            for (uint32_t g0 = 0; g0 < nu; g0 += kProbes) {
+                const uint32_t ng = nu - g0;  // live groups of this round (uniform), >= 1
+                int bp[kProbes];
+                uint64_t h[kProbes];
+                uint32_t slot[kProbes];
 #pragma unroll
-            for (int u = 0; u < kProbes; ++u) {
-                const uint32_t li = lane + 32 * u;
-                if (u < nu && li < i1 - i0) {
-                    const uint32_t flags = uint32_t(word[u] >> fsh);  // bit 1: slope +1, bit 0: colliding
-                    const int32_t ns = (flags & 1u) ? 0 : ((flags & 2u) ? -1 : 1);
-                    const uint64_t B = (word[u] & bmask) - uint64_t(int64_t(ns) * bp[u]);
-                    const uint32_t lo = uint32_t(B), hi = uint32_t(B >> 32);
-                    if (u == 0) { hi0 = hi; have = true; }
-                    special |= ns == 0 || hi != hi0 || lo - 1024u >= 0xFFFFF800u;  // needs 64-bit care
-                    s_ent[li] = Entry{lo, ns};
-                    s_hi[li] = hi;
-                    s_ref[bp[u]] = uint8_t(li);
+                for (int u = 0; u < kProbes; ++u) {
+                    if (u < ng) {
+                        const uint32_t li = lane + 32 * (g0 + u);
+                        bp[u] = s_list[li < n_chunk ? li : 0];  // dead lanes redo entry 0 (harmless)
+                        h[u] = murmur64(mmer_at<M>(s_packed, bp[u]), P.seed);
+                        slot[u] = phf_bucket(P, h[u]);
+                    }
+                }
+                uint64_t hp[kProbes];
+#pragma unroll
+                for (int u = 0; u < kProbes; ++u)
+                    if (u < ng) hp[u] = ldg_keep(P.pilot_hash + slot[u], keep);
+                // the bucket table is indexed by the raw table slot (free slots folded in at load time)
+                uint64_t word[kProbes];
+#pragma unroll
+                for (int u = 0; u < kProbes; ++u) {
+                    if (u < ng) {
+                        const uint32_t ts = phf_table_slot(P, h[u] ^ hp[u]);
+                        if (f.buckets.wide) word[u] = ldg_keep(reinterpret_cast<const uint64_t*>(f.buckets.entries) + ts, keep);
+                        else word[u] = ldg_keep(reinterpret_cast<const uint32_t*>(f.buckets.entries) + ts, keep);
+                    }
+                }
+                // bucket word -> {B, ns}: hval = base + slope * (bp - q) = (base + slope * bp) + (-slope) * q
+#pragma unroll
+                for (int u = 0; u < kProbes; ++u) {
+                    const uint32_t li = lane + 32 * (g0 + u);
+                    if (u < ng && li < n_chunk) {
+                        const uint32_t flags = uint32_t(word[u] >> fsh);  // bit 1: slope +1, bit 0: colliding
+                        const int32_t ns = (flags & 1u) ? 0 : ((flags & 2u) ? -1 : 1);
+                        const uint64_t B = (word[u] & bmask) - uint64_t(int64_t(ns) * bp[u]);
+                        const uint32_t lo = uint32_t(B), hi = uint32_t(B >> 32);
+                        if (!have) { hi0 = hi; have = true; }
+                        special |= ns == 0 || hi != hi0 || lo - 1024u >= 0xFFFFF800u;  // needs 64-bit care
+                        s_ent[li] = Entry{lo, ns};
+                        s_hi[li] = hi;
+                        s_ref[bp[u]] = uint8_t(li);
+                    }
                 }
             }
-        }
-        // plain emit needs: every entry of the warp shares lane 0's high word and cannot carry, no
-        // colliding minimizer, no start without a code in the warp's range, one chunk
-        const uint32_t hi_warp = __shfl_sync(0xFFFFFFFFu, hi0, 0);
-        special |= have && hi0 != hi_warp;
-        const bool plain = !chunked && !warp_has_invalid && !__any_sync(0xFFFFFFFFu, special);
-        __syncwarp();
-        if (plain) emit_plain(lane, s_pos, s_ref, s_ent, hi_warp, out + wbase - s_invpre[wbase >> 5]);
-        else if (!chunked) emit_general<false>(lane, wbase, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_list, s_n_fb, s_invalid, s_invpre, out);
-        else emit_general<true>(lane, wbase, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_list, s_n_fb, s_invalid, s_invpre, out);
-        __syncwarp();
+            // plain emit needs: every entry of the tile shares lane 0's high word and cannot carry, no
+            // colliding minimizer, no start without a code, one chunk
+            const uint32_t hi_warp = __shfl_sync(0xFFFFFFFFu, hi0, 0);
+            special |= have && hi0 != hi_warp;
+            const bool plain = !chunked && !tile_has_invalid && !__any_sync(0xFFFFFFFFu, special);
+            __syncwarp();
+            if (plain) emit_plain(lane, s_pos, s_ref, s_ent, hi_warp, out);
+            else if (!chunked) emit_general<false>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
+            else emit_general<true>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
+            __syncwarp();
 
-        // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
-        // (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134)
-        const uint32_t n_fb = *s_n_fb;
-        for (uint32_t e = lane; e < n_fb; e += 32) {
-            const int g = wbase + s_list[e];
-            const int wi = g >> 4, r = (g & 15) * 2;
-            uint32_t x[6];
+            // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
+            // (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134)
+            uint32_t fbw = lane < kMaskWords ? s_fbmask[lane] : 0u;  // lane l owns k-mers 32 l .. 32 l + 31
+            if (fbw) s_fbmask[lane] = 0;
+            while (fbw) {
+                const int g = lane * 32 + (__ffs(fbw) - 1);
+                fbw &= fbw - 1;
+                const int wi = g >> 4, r = (g & 15) * 2;
+                uint32_t x[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
-            uint32_t y[5];
+                for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
+                uint32_t y[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], r);
-            // y[0..3] = 128-bit window starting at base g (y[0] most significant)
-            uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
-            uint64_t klo, khi;
-            if constexpr (K <= 32) {
-                klo = top >> (64 - 2 * K);
-                khi = 0;
-                (void)bot;
-            } else {
-                constexpr int sh = 128 - 2 * K;  // 2..62
-                klo = (bot >> sh) | (top << (64 - sh));
-                khi = top >> sh;
+                for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], r);
+                // y[0..3] = 128-bit window starting at base g (y[0] most significant)
+                uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
+                uint64_t klo, khi;
+                if constexpr (K <= 32) {
+                    klo = top >> (64 - 2 * K);
+                    khi = 0;
+                    (void)bot;
+                } else {
+                    constexpr int sh = 128 - 2 * K;  // 2..62
+                    klo = (bot >> sh) | (top << (64 - sh));
+                    khi = top >> sh;
+                }
+                const uint32_t mw = s_invalid[g >> 5];
+                const int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
+                out[oidx] = fallback_code(f, klo, khi);
             }
-            uint32_t mw = s_invalid[g >> 5];
-            int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
-            out[oidx] = fallback_code(f, klo, khi);
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) *s_n_fb = 0;
-        __syncwarp();
-    }
+    }  // tiles of this warp
 }
 
-// per tile: contig containing its first in-range position + number of valid k-mer starts before it
+// per tile: contig containing its first in-range position, number of valid k-mer starts before it,
+// and whether one contig covers the tile plus k-1 bases (then every start yields a code)
 __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, uint32_t n_tiles,
-                             uint32_t k, uint32_t* tile_c0, uint64_t* tile_out) {
+                             uint32_t k, TileRec* recs) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    int64_t p = pos0 + int64_t(t) * kTile;
+    const int64_t t0 = pos0 + int64_t(t) * kTile;
+    int64_t p = t0;
     if (p < int64_t(b.first_base)) p = int64_t(b.first_base);
     uint64_t lo = 0, hi = b.n_contigs;  // offsets[lo] <= p (offsets[0] = first_base <= p)
     while (hi - lo > 1) {
@@ -612,25 +717,37 @@ __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, u
     uint64_t s = __ldg(b.offsets + lo), e = __ldg(b.offsets + lo + 1);
     uint64_t len = e - s, cnt = len >= k ? len - k + 1 : 0;
     uint64_t before = uint64_t(p) - s;
-    tile_c0[t] = uint32_t(lo);
-    tile_out[t] = __ldg(b.code_off + lo) + (before < cnt ? before : cnt);
+    TileRec r;
+    r.c0 = uint32_t(lo);
+    r.out = __ldg(b.code_off + lo) + (before < cnt ? before : cnt);
+    r.clean = (t0 >= int64_t(b.first_base) && int64_t(s) <= t0 && int64_t(e) >= t0 + kTile + int64_t(k) - 1) ? 1u : 0u;
+    recs[t] = r;
 }
 
 template <int K, int M>
 void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaStream_t stream) {
     static bool configured = false;  // per instantiation; the attribute is per device function
+    static int resident = 0;         // CTAs that fit the device at once
     if (!configured) {
         cudaFuncSetAttribute(k_query_tiled<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query_tiled<K, M>, kThreads, kSmemBytes);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
         configured = true;
     }
-    k_query_tiled<K, M><<<a.n_tiles, kThreads, kSmemBytes, stream>>>(img, b, a);
+    // persistent grid: every warp walks tiles (global warp id) + i * (number of warps)
+    const uint32_t ctas_needed = (a.n_tiles + kWarps - 1) / kWarps;
+    const uint32_t grid = ctas_needed < uint32_t(resident) ? ctas_needed : uint32_t(resident);
+    k_query_tiled<K, M><<<grid, kThreads, kSmemBytes, stream>>>(img, b, a);
 }
 
 }  // namespace
 
 uint64_t query_tiled_ws_bytes(uint64_t span_bases) {
     uint64_t n_tiles = (span_bases + 16) / kTile + 2;
-    return n_tiles * 12 + 64;
+    return n_tiles * sizeof(TileRec) + 64;
 }
 
 bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream) {
@@ -653,13 +770,13 @@ bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t str
     a.abase = p - ali;
     a.pos0 = int64_t(b.first_base) - int64_t(ali);
     uint64_t span = uint64_t(int64_t(b.end_base) - a.pos0);
-    a.n_tiles = uint32_t((span + kTile - 1) / kTile);
+    uint64_t n_tiles = (span + kTile - 1) / kTile;
+    if (n_tiles >= (1ull << 31)) return false;
+    a.n_tiles = uint32_t(n_tiles);
     if (query_tiled_ws_bytes(b.end_base - b.first_base) > b.tile_ws_bytes) return false;
-    uint64_t* tile_out = reinterpret_cast<uint64_t*>(b.tile_ws);
-    uint32_t* tile_c0 = reinterpret_cast<uint32_t*>(tile_out + a.n_tiles + 1);
-    a.tile_out = tile_out;
-    a.tile_c0 = tile_c0;
-    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, k, tile_c0, tile_out);
+    TileRec* recs = reinterpret_cast<TileRec*>(b.tile_ws);
+    a.recs = recs;
+    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, k, recs);
     fn(img, b, a, stream);
     return true;
 }
