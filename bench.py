@@ -90,43 +90,54 @@ def rotate_contigs(bases, offsets, r: int):
 # ---------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + clock-event reasons of one GPU, polled through NVML from a thread every ~1 ms
+    while the timed region runs (the region is tens of ms: `nvidia-smi -lms` is too coarse)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.bits = [], 0
+        self.max_sm = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        self._nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self._nv = nv
+            self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = int(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # no NVML: report no samples rather than fail the bench
+            log(f"[bench] NVML unavailable: {e}")
+            self._h = None
+            return
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
+    def _poll(self):
+        nv = self._nv
+        while not self._stop.is_set():
             try:
-                self.proc.wait(timeout=2)
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except AttributeError:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
             except Exception:
                 pass
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
-                          if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+            time.sleep(0.001)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -244,22 +255,21 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
+    f.stats()  # drop the warm-up launches from the handle's per-launch event ring
     sync_all()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     sync_all()
+    clocks = sampler.stop() if rank == 0 else None  # polled during the timed region only
     ms_total = ev0.elapsed_time(ev1)
-    launches_per_step = int(f.stats().kernel_launches)
-    # dominant-kernel launch time: the handle brackets its main kernel with CUDA events on the
-    # launching stream; sample it over a few extra steps (outside the timed region)
-    for _ in range(min(args.steps, 5)):
-        step()
-        kernel_ms.append(f.stats().kernel_ms)
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    # dominant-kernel launch time: the handle brackets its main kernel with a CUDA-event pair on
+    # the launching stream at EVERY call; stats() returns the mean over the timed region's
+    # launches (the most recent 128 of them)
+    st_timed = f.stats()
+    launches_per_step = int(st_timed.kernel_launches)
+    kernel_ms = [float(st_timed.kernel_ms)]
 
     # ---- e2e: HOST (pinned) buffers through lphb_query_stream -----------------------------
     h_bases = torch.from_numpy(bases).pin_memory()
@@ -300,6 +310,13 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None  # dram bytes read + written by the dominant kernel, from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("kmers_per_launch") == n_kmers:
+                traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
+        except Exception:
+            pass
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         line = {"metric": "query-p k-mers/sec (k=31)", "value": value, "unit": "k-mers/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -312,8 +329,9 @@ def run_ours(args):
                         "api": "lphb_query_stream (pinned host buffers)"},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None,
-                             "kernel": "dominant query kernel (per launch, CUDA events on the launching stream)",
+                             "frac": achieved / peak, "traffic": traffic,
+                             "kernel": "k_query_tiled<31,20> (mean per launch over the timed region, CUDA events on the launching stream)",
+                             "traffic_source": "profiles/traffic.json (ncu --set full, one launch)" if traffic else None,
                              "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "input_only_frac": (algo_bytes - 8 * n_kmers) / (kern_ms * 1e-3) / 1e9 / peak},
@@ -337,7 +355,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kmers", type=int, default=100_000_000)

@@ -122,7 +122,8 @@ typedef struct lphb_stats {
     uint64_t kernel_launches;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t dirty_contigs;
-    double kernel_ms; /* CUDA-event time of the main kernel(s), host-buffer calls only */
+    double kernel_ms; /* mean CUDA-event time of the main query kernel over the calls since the last
+                         lphb_mphf_stats (most recent 128) */
 } lphb_stats;
 int lphb_mphf_stats(const lphb_mphf* f, lphb_stats* stats);
 

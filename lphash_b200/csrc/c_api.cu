@@ -62,12 +62,17 @@ struct Workspace {
     DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
     unsigned long long* h_status = nullptr;  // pinned, 4 words
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // ring of event pairs bracketing the main kernel of the last kEvRing calls
+    static constexpr int kEvRing = 128;
+    cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+    uint64_t ev_next = 0, ev_pending = 0;  // next slot; pairs recorded since the last stats read
     void init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaMallocHost(reinterpret_cast<void**>(&h_status), 4 * sizeof(unsigned long long)));
-        CK(cudaEventCreate(&ev0));
-        CK(cudaEventCreate(&ev1));
+        for (int i = 0; i < kEvRing; ++i) {
+            CK(cudaEventCreate(&ev0[i]));
+            CK(cudaEventCreate(&ev1[i]));
+        }
         status.reserve(4 * sizeof(unsigned long long));
     }
     void destroy() {
@@ -75,8 +80,10 @@ struct Workspace {
                           &aux2, &aux3, &codes2, &tile})
             b->release();
         if (h_status) cudaFreeHost(h_status);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < kEvRing; ++i) {
+            if (ev0[i]) cudaEventDestroy(ev0[i]);
+            if (ev1[i]) cudaEventDestroy(ev1[i]);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -103,7 +110,6 @@ struct lphb_mphf {
     bool l2_stream_set = false;
     lphb_info info{};
     lphb_stats stats{};
-    bool events_pending = false;
     Workspace ws;
 };
 
@@ -219,10 +225,12 @@ void attach_l2_window(lphb_mphf* f, cudaStream_t s) {
 
 void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
     attach_l2_window(f, s);
-    CK(cudaEventRecord(f->ws.ev0, s));
+    const int slot = int(f->ws.ev_next % Workspace::kEvRing);
+    CK(cudaEventRecord(f->ws.ev0[slot], s));
     if (!launch_query_tiled(f->img, b, s)) launch_query_generic(f->img, b, s);
-    CK(cudaEventRecord(f->ws.ev1, s));
-    f->events_pending = true;
+    CK(cudaEventRecord(f->ws.ev1[slot], s));
+    ++f->ws.ev_next;
+    ++f->ws.ev_pending;
     launch_count_dirty(b.dirty, b.n_contigs, b.status, s);
     f->stats.kernel_launches += 2;
 }
@@ -283,14 +291,26 @@ int lphb_mphf_info(const lphb_mphf* f, lphb_info* info) {
 int lphb_mphf_stats(const lphb_mphf* cf, lphb_stats* stats) {
     if (!cf || !stats) return fail(LPHB_E_ARG, "null argument");
     auto* f = const_cast<lphb_mphf*>(cf);
-    if (f->events_pending) {  // device time of the last main kernel (waits for it to finish)
-        float ms = 0;
-        if (cudaEventSynchronize(f->ws.ev1) == cudaSuccess &&
-            cudaEventElapsedTime(&ms, f->ws.ev0, f->ws.ev1) == cudaSuccess)
-            f->stats.kernel_ms = ms;
-        else
-            cudaGetLastError();
-        f->events_pending = false;
+    if (f->ws.ev_pending) {
+        // mean device time of the main kernel over the calls made since the last stats read (at
+        // most the kEvRing most recent); waits for the last of them to finish
+        Workspace& ws = f->ws;
+        uint64_t n = ws.ev_pending < uint64_t(Workspace::kEvRing) ? ws.ev_pending : uint64_t(Workspace::kEvRing);
+        double sum = 0;
+        uint64_t got = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            const int slot = int((ws.ev_next - 1 - i) % Workspace::kEvRing);
+            float ms = 0;
+            if (cudaEventSynchronize(ws.ev1[slot]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, ws.ev0[slot], ws.ev1[slot]) == cudaSuccess) {
+                sum += ms;
+                ++got;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (got) f->stats.kernel_ms = sum / double(got);
+        ws.ev_pending = 0;
     }
     *stats = f->stats;
     return LPHB_OK;
