@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
@@ -62,6 +63,18 @@ struct Workspace {
     DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
     unsigned long long* h_status = nullptr;  // pinned, 4 words
     cudaStream_t stream = nullptr;
+    // chunk pipeline of lphb_query_stream: two extra streams so that the H2D copy of chunk j+1,
+    // the kernels of chunk j and the D2H copy of chunk j-1 overlap (PCIe is full duplex)
+    cudaStream_t cs[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr, ev_done[2] = {nullptr, nullptr};
+    void ensure_pipeline() {
+        if (cs[0]) return;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaStreamCreateWithFlags(&cs[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    }
     // ring of event pairs bracketing the main kernel of the last kEvRing calls
     static constexpr int kEvRing = 128;
     cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
@@ -85,8 +98,20 @@ struct Workspace {
             if (ev1[i]) cudaEventDestroy(ev1[i]);
         }
         if (stream) cudaStreamDestroy(stream);
+        for (int i = 0; i < 2; ++i) {
+            if (cs[i]) cudaStreamDestroy(cs[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+        }
+        if (ev_ready) cudaEventDestroy(ev_ready);
     }
 };
+
+// bases per chunk of the lphb_query_stream pipeline (LPHB_CHUNK_BASES overrides; 0 disables)
+uint64_t pipeline_chunk_bases() {
+    const char* e = getenv("LPHB_CHUNK_BASES");  // read per call: tests vary it
+    uint64_t x = e ? strtoull(e, nullptr, 10) : (uint64_t(8) << 20);
+    return x ? x : ~uint64_t(0);
+}
 
 bool is_host_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -106,8 +131,7 @@ struct lphb_mphf {
     uint64_t arena_bytes = 0;
     uint64_t l2_window_bytes = 0;      // 0: persistence not available
     float l2_hit_ratio = 1.0f;         // share of the window that may persist (carve-out / window)
-    cudaStream_t l2_stream = nullptr;  // last stream the window was attached to
-    bool l2_stream_set = false;
+    std::vector<cudaStream_t> l2_streams;  // streams the window is attached to
     lphb_info info{};
     lphb_stats stats{};
     Workspace ws;
@@ -172,6 +196,7 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
                 if (uint64_t(max_window) < window) window = uint64_t(max_window);
                 uint64_t carve = window;
                 if (uint64_t(max_persist) < carve) carve = uint64_t(max_persist);
+                if (getenv("LPHB_NO_L2_WINDOW")) carve = 0;  // tuning switch
                 if (carve && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
                     f->l2_window_bytes = window;
                     f->l2_hit_ratio = float(double(carve) / double(window));
@@ -210,7 +235,9 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
 // Keep the image (a few bits per k-mer, gathered at random) resident in L2 while the base stream
 // and the codes (streamed once, marked evict-first in the kernels) flow through it.
 void attach_l2_window(lphb_mphf* f, cudaStream_t s) {
-    if (!f->l2_window_bytes || (f->l2_stream_set && f->l2_stream == s)) return;
+    if (!f->l2_window_bytes) return;
+    for (cudaStream_t t : f->l2_streams)
+        if (t == s) return;
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = f->d_arena;
     attr.accessPolicyWindow.num_bytes = f->l2_window_bytes;
@@ -219,8 +246,8 @@ void attach_l2_window(lphb_mphf* f, cudaStream_t s) {
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
         cudaGetLastError();  // a hint only
-    f->l2_stream = s;
-    f->l2_stream_set = true;
+    if (f->l2_streams.size() >= 16) f->l2_streams.clear();  // caller cycles through many streams
+    f->l2_streams.push_back(s);
 }
 
 void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
@@ -404,7 +431,6 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         ws.code_off.reserve((n_contigs + 1) * 8);
         ws.codes.reserve(total * 8 + 64);
         ws.dirty.reserve(n_contigs + 8);
-        CK(cudaMemcpyAsync(ws.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ws.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ws.code_off.p, code_offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ws.dirty.p, 0, n_contigs + 8, s));
@@ -420,10 +446,62 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         b.codes = ws.codes.as<uint64_t>();
         b.dirty = ws.dirty.as<uint8_t>();
         b.status = ws.status.as<unsigned long long>();
-        ws.tile.reserve(query_tiled_ws_bytes(span));
-        b.tile_ws = ws.tile.p;
-        b.tile_ws_bytes = ws.tile.cap;
-        run_kernels(f, b, s);
+        // Large batches are cut (on contig boundaries) into chunks that flow through two streams:
+        // H2D of chunk j+1, the kernels of chunk j and the D2H of chunk j-1's codes overlap.  The
+        // codes are copied out optimistically in the clean layout; if some contig turns out to
+        // contain a non-ACGT byte the quirk path below rewrites the host buffer.
+        std::vector<uint64_t> cuts{0};
+        {
+            const uint64_t chunk = pipeline_chunk_bases();
+            for (uint64_t c = 0; c < n_contigs; ++c)
+                if (offsets[c + 1] - offsets[cuts.back()] >= chunk && c + 1 < n_contigs) cuts.push_back(c + 1);
+            cuts.push_back(n_contigs);
+        }
+        const bool pipelined = cuts.size() > 2 && total <= codes_capacity && codes;
+        if (!pipelined) {
+            CK(cudaMemcpyAsync(ws.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
+            ws.tile.reserve(query_tiled_ws_bytes(span));
+            b.tile_ws = ws.tile.p;
+            b.tile_ws_bytes = ws.tile.cap;
+            run_kernels(f, b, s);
+        } else {
+            ws.ensure_pipeline();
+            const uint64_t n_chunks = cuts.size() - 1;
+            std::vector<uint64_t> tile_at(n_chunks + 1, 0);
+            for (uint64_t j = 0; j < n_chunks; ++j) {
+                uint64_t bytes = query_tiled_ws_bytes(offsets[cuts[j + 1]] - offsets[cuts[j]]);
+                tile_at[j + 1] = tile_at[j] + (bytes + 255) / 256 * 256;
+            }
+            ws.tile.reserve(tile_at[n_chunks]);
+            CK(cudaEventRecord(ws.ev_ready, s));
+            for (uint64_t j = 0; j < n_chunks; ++j) {
+                cudaStream_t st = ws.cs[j & 1];
+                if (j < 2) CK(cudaStreamWaitEvent(st, ws.ev_ready, 0));
+                const uint64_t c0 = cuts[j], c1 = cuts[j + 1];
+                const uint64_t b0 = offsets[c0], b1 = offsets[c1];
+                if (b1 > b0)
+                    CK(cudaMemcpyAsync(ws.bases.as<char>() + (b0 - first), bases + b0, b1 - b0,
+                                       cudaMemcpyHostToDevice, st));
+                DevBatch bj = b;
+                bj.offsets = b.offsets + c0;
+                bj.code_off = b.code_off + c0;
+                bj.n_contigs = c1 - c0;
+                bj.first_base = b0;
+                bj.end_base = b1;
+                bj.dirty = b.dirty + c0;
+                bj.tile_ws = static_cast<char*>(ws.tile.p) + tile_at[j];
+                bj.tile_ws_bytes = tile_at[j + 1] - tile_at[j];
+                run_kernels(f, bj, st);
+                const uint64_t o0 = code_offsets[c0], o1 = code_offsets[c1];
+                if (o1 > o0)
+                    CK(cudaMemcpyAsync(codes + o0, ws.codes.as<uint64_t>() + o0, (o1 - o0) * 8,
+                                       cudaMemcpyDeviceToHost, st));
+            }
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaEventRecord(ws.ev_done[i], ws.cs[i]));
+                CK(cudaStreamWaitEvent(s, ws.ev_done[i], 0));
+            }
+        }
         CK(cudaMemcpyAsync(ws.h_status, ws.status.p, 4 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -432,8 +510,10 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         f->stats.dirty_contigs = n_dirty;
         if (n_dirty == 0) {
             if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
-            if (total) CK(cudaMemcpyAsync(codes, ws.codes.p, total * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            if (total && !pipelined) {
+                CK(cudaMemcpyAsync(codes, ws.codes.p, total * 8, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+            }
             f->stats.d2h_bytes = total * 8 + 32;
             return LPHB_OK;
         }

@@ -28,9 +28,10 @@ namespace lphb {
 
 struct DevPhf {              // pthash::single_phf<*, dictionary_dictionary, true>
     uint64_t seed, num_keys, table_size;
-    uint64_t dense, sparse;  // skew_bucketer bucket counts (bucketers.hpp:10-22); all < 2^32
-    // 96-bit reciprocals ceil(2^96/d) (exact a % d for 64-bit a and d < 2^32)
-    uint32_t m_table[3], m_dense[3], m_sparse[3];
+    uint64_t dense, sparse;  // skew_bucketer bucket counts (bucketers.hpp:10-22); all < 2^31
+    // 64-bit reciprocals floor(2^64/d) as two 32-bit limbs (exact a % d for 64-bit a and d < 2^31,
+    // device_mphf.cuh: mod_small)
+    uint32_t m_table[2], m_dense[2], m_sparse[2];
     const uint64_t* pilot_hash;  // per bucket: default_hash64(pilot, seed)
     const uint32_t* free32;  // free32[i] == free_slots.access(i)
 };

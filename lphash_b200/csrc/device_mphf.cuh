@@ -28,23 +28,19 @@ LPHB_DEV uint64_t murmur64(uint64_t v, uint64_t seed) {
     return h;
 }
 
-// a % d for 64-bit a and d < 2^32 with M = ceil(2^96 / d) (three 32-bit limbs).
-// The reference computes fastmod_u64(a, ceil(2^128/d), d) (pthash/external/fastmod/fastmod.h:
-// 56-63, 159-162), which equals a % d exactly; so does this 96-bit variant
-// (Lemire-Kaser-Kurz: exact when fraction bits >= 64 + log2 d).
-LPHB_DEV uint32_t mod_small(uint64_t a, uint32_t M0, uint32_t M1, uint32_t M2, uint32_t d) {
-    uint32_t a0 = uint32_t(a), a1 = uint32_t(a >> 32);
-    uint64_t p00 = uint64_t(M0) * a0;
-    uint64_t p01 = uint64_t(M0) * a1;
-    uint64_t p10 = uint64_t(M1) * a0;
-    uint32_t l0 = uint32_t(p00);
-    uint64_t t1 = (p00 >> 32) + uint32_t(p01) + uint32_t(p10);
-    uint32_t l1 = uint32_t(t1);
-    uint32_t l2 = uint32_t(t1 >> 32) + uint32_t(p01 >> 32) + uint32_t(p10 >> 32) + M1 * a1 + M2 * a0;
-    uint64_t q = (uint64_t(l0) * d) >> 32;
-    q = (uint64_t(l1) * d + q) >> 32;
-    q = (uint64_t(l2) * d + q) >> 32;
-    return uint32_t(q);
+// a % d for 64-bit a and d < 2^31, with M = floor(2^64 / d) as two 32-bit limbs.
+// q' = floor(a * M / 2^64) is floor(a / d) or one less (a * M / 2^64 lies in (a/d - 1, a/d]), so
+// a - q' * d lies in [0, 2d) and fits 32 bits: only the low word of q' is needed, hence only bits
+// 32..63 of the middle partial products (their wrap-around past 2^64 is irrelevant), and one
+// unsigned min folds the remainder.  The reference computes fastmod_u64(a, ceil(2^128/d), d)
+// (pthash/external/fastmod/fastmod.h:56-63, 159-162), which is a % d exactly; so is this.
+LPHB_DEV uint32_t mod_small(uint64_t a, uint32_t M0, uint32_t M1, uint32_t d) {
+    const uint32_t a0 = uint32_t(a), a1 = uint32_t(a >> 32);
+    uint64_t s = uint64_t(a1) * M0 + __umulhi(a0, M0);
+    s += uint64_t(a0) * M1;
+    const uint32_t q = a1 * M1 + uint32_t(s >> 32);
+    const uint32_t r = a0 - q * d;
+    return min(r, r - d);
 }
 
 // Gathers from the image carry an L2 evict_last policy: the image (a few bytes per minimizer,
@@ -55,6 +51,11 @@ LPHB_DEV uint64_t l2_keep_policy() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+#ifdef LPHB_NOHINT  // tuning experiment: plain read-only loads without the L2 policy
+LPHB_DEV uint32_t ldg_keep(const uint32_t* p, uint64_t) { return __ldg(p); }
+LPHB_DEV uint32_t ldg_keep(const uint16_t* p, uint64_t) { return __ldg(p); }
+LPHB_DEV uint64_t ldg_keep(const uint64_t* p, uint64_t) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+#else
 LPHB_DEV uint32_t ldg_keep(const uint32_t* p, uint64_t pol) {
     uint32_t v;
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -70,6 +71,7 @@ LPHB_DEV uint64_t ldg_keep(const uint64_t* p, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     return v;
 }
+#endif
 
 // pthash::single_phf::position, in the stages a caller may interleave across several keys.
 // ref: pthash/include/single_phf.hpp:55-65; skew_bucketer::bucket pthash/include/utils/
@@ -82,11 +84,10 @@ LPHB_DEV uint32_t phf_bucket(DevPhf const& p, uint64_t h) {
     const uint32_t d = dn ? uint32_t(p.dense) : uint32_t(p.sparse);
     const uint32_t r0 = dn ? p.m_dense[0] : p.m_sparse[0];
     const uint32_t r1 = dn ? p.m_dense[1] : p.m_sparse[1];
-    const uint32_t r2 = dn ? p.m_dense[2] : p.m_sparse[2];
-    return mod_small(h, r0, r1, r2, d) + (dn ? 0u : uint32_t(p.dense));
+    return mod_small(h, r0, r1, d) + (dn ? 0u : uint32_t(p.dense));
 }
 LPHB_DEV uint32_t phf_table_slot(DevPhf const& p, uint64_t h_xor_pilot) {
-    return mod_small(h_xor_pilot, p.m_table[0], p.m_table[1], p.m_table[2], uint32_t(p.table_size));
+    return mod_small(h_xor_pilot, p.m_table[0], p.m_table[1], uint32_t(p.table_size));
 }
 LPHB_DEV uint64_t phf_position(DevPhf const& p, uint64_t h) {
     const uint32_t pos = phf_table_slot(p, h ^ __ldg(p.pilot_hash + phf_bucket(p, h)));

@@ -206,13 +206,11 @@ void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits 
     }
 }
 
-void reciprocal96(uint64_t d, uint32_t out[3]) {
-    // M = floor((2^96 - 1) / d) + 1 via long division on 32-bit limbs
-    unsigned __int128 num = (((unsigned __int128)1) << 96) - 1;
-    unsigned __int128 M = num / d + 1;
+void reciprocal64(uint64_t d, uint32_t out[2]) {
+    // M = floor(2^64 / d); d == 1 uses 2^64 - 1 (mod_small still returns 0)
+    unsigned __int128 M = d > 1 ? ((((unsigned __int128)1) << 64) / d) : ((((unsigned __int128)1) << 64) - 1);
     out[0] = uint32_t(M);
     out[1] = uint32_t(M >> 32);
-    out[2] = uint32_t(M >> 64);
 }
 
 void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
@@ -249,11 +247,13 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
         per_bucket[b] = hp[r];
     }
     out.pilot_hash = append(per_bucket.data(), nbuckets, 2);
-    if (out.table_size >= (1ull << 32) || out.dense >= (1ull << 32) || out.sparse >= (1ull << 32))
-        throw FormatError("single_phf: table larger than 2^32 (impossible with 64-bit PTHash hashes)");
-    reciprocal96(out.table_size, out.m_table);
-    reciprocal96(out.dense, out.m_dense);
-    reciprocal96(out.sparse, out.m_sparse);
+    // 64-bit PTHash hashes cap num_keys at 2^30 (hasher.hpp:27-31), so table_size = num_keys/alpha
+    // stays below 2^31, which the device-side exact modulo relies on
+    if (out.table_size >= (1ull << 31) || out.dense >= (1ull << 31) || out.sparse >= (1ull << 31))
+        throw FormatError("single_phf: table larger than 2^31 (impossible with 64-bit PTHash hashes)");
+    reciprocal64(out.table_size, out.m_table);
+    reciprocal64(out.dense, out.m_dense);
+    reciprocal64(out.sparse, out.m_sparse);
     // minimal remap as a plain array: one load instead of an Elias-Fano select
     std::vector<uint64_t> free_vals = read_ef(c);
     if (free_vals.size() != out.table_size - out.num_keys)

@@ -626,13 +626,21 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                 uint64_t hp[kProbes];
 #pragma unroll
                 for (int u = 0; u < kProbes; ++u)
+#ifdef LPHB_EXP_NOGATHER  // timing experiment only (wrong codes): no image reads
+                    if (u < ng) hp[u] = h[u] + slot[u];
+#else
                     if (u < ng) hp[u] = ldg_keep(P.pilot_hash + slot[u], keep);
+#endif
                 // the bucket table is indexed by the raw table slot (free slots folded in at load time)
                 uint64_t word[kProbes];
 #pragma unroll
                 for (int u = 0; u < kProbes; ++u) {
                     if (u < ng) {
                         const uint32_t ts = phf_table_slot(P, h[u] ^ hp[u]);
+#ifdef LPHB_EXP_NOGATHER
+                        word[u] = (ts & 0x3FFFFFFFu) | 0x80000000u;
+                        continue;
+#endif
                         if (f.buckets.wide) word[u] = ldg_keep(reinterpret_cast<const uint64_t*>(f.buckets.entries) + ts, keep);
                         else word[u] = ldg_keep(reinterpret_cast<const uint32_t*>(f.buckets.entries) + ts, keep);
                     }

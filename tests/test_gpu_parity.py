@@ -96,6 +96,25 @@ def test_random_reads_match_oracle(name, handles):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("chunk", [1, 700, 5000, 1 << 16])
+def test_chunk_pipeline_matches_single_batch(golden, handles, chunk, monkeypatch):
+    """lphb_query_stream cuts large batches into chunks that flow through two streams (H2D /
+    kernels / D2H overlapped); any chunk size must give the single-batch result, with and
+    without contigs that take the non-ACGT quirk path."""
+    f = handles(golden.name)
+    monkeypatch.setenv("LPHB_CHUNK_BASES", str(chunk))
+    codes, code_off = f.query_batch(golden.q_bases, golden.q_offsets)
+    assert np.array_equal(code_off, golden.q_code_offsets)
+    assert np.array_equal(codes, golden.q_codes)
+    codes, code_off = f.query_batch(golden.index_bases, golden.index_offsets)
+    assert f.stats().dirty_contigs == 0
+    n = f.get_kmer_count()
+    assert len(codes) == n and np.array_equal(np.sort(codes), np.arange(n, dtype=np.uint64))
+    monkeypatch.setenv("LPHB_CHUNK_BASES", "0")  # pipeline off
+    ref_codes, ref_off = f.query_batch(golden.index_bases, golden.index_offsets)
+    assert np.array_equal(codes, ref_codes) and np.array_equal(code_off, ref_off)
+
+
 def test_capacity_error(handles):
     g = load_golden("k31_m20_u64")
     f = handles(g.name)
