@@ -31,7 +31,7 @@ if has launches; then
   echo "launches exit $?"
 fi
 if has full; then
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_query_tiled -s 3 -c 1 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_query_ -s 3 -c 1 \
     -f -o "$OUT/prof_query_tiled" python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$OUT/full_bench.log" 2>&1
   echo "full exit $?"; ls -la "$OUT"
 fi

@@ -22,7 +22,7 @@ def main():
             hdr = r
         elif r[0] not in ("", "Function Name") and hdr and r[0].isdigit():
             def num(name):
-                v = r[hdr.index(name)]
+                v = r[hdr.index(name) - len(hdr)]
                 return int(v) if v.lstrip("-").isdigit() else 0
             agg.append((cur, int(r[0]), r[1].strip(), num("Instructions Executed"), num("# Samples")))
     tot = sum(a[3] for a in agg) or 1

@@ -16,7 +16,7 @@ def main():
         elif r[0] == "Line No": hdr = r
         elif hdr and r[0].isdigit():
             def num(name):
-                v = r[hdr.index(name)]
+                v = r[hdr.index(name) - len(hdr)]
                 return int(v) if v.lstrip("-").isdigit() else 0
             agg.append((cur, int(r[0]), num("Instructions Executed"), num("# Samples")))
     tot = sum(a[2] for a in agg) or 1
