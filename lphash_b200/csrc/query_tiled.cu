@@ -39,7 +39,6 @@
 // k-1 bases of read overlap and nothing else.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "device_mphf.cuh"
 #include "query_kernels.cuh"
@@ -51,12 +50,12 @@ namespace {
 constexpr int kWarps = 4;                      // warps per CTA (independent of each other)
 constexpr int kThreads = kWarps * 32;
 constexpr int kS = 16;                         // k-mer starts per thread = bases per packed word
-constexpr int kLanes = 31;                     // producing lanes per warp (lane 31 only feeds lane 30)
-constexpr int kStrip = kLanes * kS;            // 496 k-mer starts per warp pass
 constexpr int kStrips = 2;                     // passes per tile
-constexpr int kTile = kStrips * kStrip;        // 992 k-mer starts per (warp) tile
-constexpr int kMaskWords = kTile / 32;         // 31 words of the invalid-start mask
-constexpr int kSlots = kTile + 32;             // positions a minimizer of the tile's k-mers can sit at
+// Per (k, m) (Cfg below): E = lanes to the right a thread's windows reach into (1 for W <= 17, up to 3
+// for W <= 49); the last E lanes of a warp only feed their neighbours, so a strip has (32 - E) * 16
+// k-mer starts and a tile 2 strips: 992 (E = 1), 960 (E = 2) or 928 (E = 3) starts.
+constexpr int kMinTile = kStrips * 29 * kS;    // smallest tile (bounds the set-up workspace)
+constexpr int kSlots = 1024;                   // positions a minimizer of the tile's k-mers can sit at (tile + < 64)
 constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
 #ifndef LPHB_PROBES
 #define LPHB_PROBES 3
@@ -178,9 +177,16 @@ struct Cfg {
     static constexpr int W = K - M + 1;
     static constexpr int NW = (kS + K - 1 + 15) / 16;        // packed words a thread reads
     static constexpr int NH = kS + W - 1;                    // m-mers under a thread's 16 windows
-    static constexpr int TileWords = kTile / 16 + NW;        // 16-byte words staged per tile
-    static_assert(W >= 1 && W <= 17, "tiled kernel: window must fit one shuffle hop");
-    static_assert(NH <= 32, "thread-local minimizer positions must fit the 5-bit key field");
+    static constexpr int E = (kS - 1 + W - 1) / 16 < 1 ? 1 : (kS - 1 + W - 1) / 16;  // neighbour lanes a window reaches
+    static constexpr int Lanes = 32 - E;                     // producing lanes per warp
+    static constexpr int Strip = Lanes * kS;                 // k-mer starts per warp pass
+    static constexpr int Tile = kStrips * Strip;             // k-mer starts per (warp) tile
+    static constexpr int MaskWords = Tile / 32;              // words of the invalid-start mask
+    static constexpr int PosBits = E == 1 ? 5 : 6;           // thread-local minimizer position field of a key
+    static constexpr int TileWords = Tile / 16 + NW;         // 16-byte words staged per tile
+    static_assert(W >= 1 && E <= 3 && Tile >= kMinTile, "tiled kernel: window must fit three shuffle hops");
+    static_assert(NH <= (1 << PosBits), "thread-local minimizer positions must fit the key's position field");
+    static_assert(Tile % 32 == 0 && Tile + (E == 1 ? 32 : 64) <= kSlots, "mask words: one per lane");
     static_assert(M <= 31 && K <= 63, "k, m out of range");
     static_assert(TileWords + 2 <= kPackedSlots && TileWords * 16 <= kRawBytes, "tile must fit its buffers");
 };
@@ -258,35 +264,23 @@ __device__ __forceinline__ uint64_t mmer_at(const uint32_t* s_packed, int g) {
 // hashes (strict '<' keeps the leftmost on ties: partitioned_mphf.hpp:124,152,159).  Taken only by
 // threads whose 27-bit keys tied; out of line.  Returns the mask of minimizer positions.
 template <int K, int M>
-static __device__ __noinline__ uint32_t exact_strip(const uint32_t* s_packed, int g0, uint64_t seed,
+static __device__ __noinline__ uint64_t exact_strip(const uint32_t* s_packed, int g0, uint64_t seed,
                                                     uint8_t* pos_out) {
     constexpr int W = K - M + 1, NH = kS + W - 1;
     uint64_t h[NH];
 #pragma unroll 1
     for (int j = 0; j < NH; ++j) h[j] = murmur64(mmer_at<M>(s_packed, g0 + j), seed);
-    uint32_t marks = 0;
+    uint64_t marks = 0;
 #pragma unroll 1
     for (int i = 0; i < kS; ++i) {
         int best = i;
         for (int j = i + 1; j < i + W; ++j)
             if (h[j] < h[best]) best = j;
         pos_out[i] = uint8_t(best);
-        marks |= 1u << best;
+        marks |= uint64_t(1) << best;
     }
     return marks;
 }
-
-// code stores: streaming (evict-first), so that the 8 B/k-mer output does not displace the image in L2
-#if defined(LPHB_EXP_NOSTORE)      // timing experiment only: the value is computed but (never) stored
-__device__ __forceinline__ void store_code(uint2* p, uint2 v) { if (v.y == 0xDEADBEEFu) *p = v; }
-__device__ __forceinline__ void store_code(uint64_t* p, uint64_t v) { if (v == 0xDEADBEEFDEADBEEFull) *p = v; }
-#elif defined(LPHB_EXP_PLAINSTORE)  // timing experiment: default cache policy
-__device__ __forceinline__ void store_code(uint2* p, uint2 v) { *p = v; }
-__device__ __forceinline__ void store_code(uint64_t* p, uint64_t v) { *p = v; }
-#else
-__device__ __forceinline__ void store_code(uint2* p, uint2 v) { __stcs(p, v); }
-__device__ __forceinline__ void store_code(uint64_t* p, uint64_t v) { __stcs(reinterpret_cast<unsigned long long*>(p), v); }
-#endif
 
 // Codes of the k-mers of a tile, position-parallel: lane l handles k-mers l, l+32, ...; two byte
 // loads find the entry of the k-mer's minimizer, code = B + ns * q, coalesced 8-byte stores.
@@ -294,19 +288,19 @@ __device__ __forceinline__ void store_code(uint64_t* p, uint64_t v) { __stcs(rei
 // Plain form, for a tile whose 992 starts all yield a code, whose entries share the high word
 // `hi` of B and cannot carry out of the low word (1024 <= lo < 2^32 - 1024), with no colliding
 // minimizer and a single chunk: one 32-bit multiply-add per code.
-template <int kUnroll>
+template <int kTile>
 __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
                                            const Entry* s_ent, uint32_t hi, uint64_t* out_tile) {
     const uint8_t* pos_l = s_pos + lane;
     const uint8_t* ref_l = s_ref + (lane & 16);
     uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
-#pragma unroll kUnroll
+#pragma unroll 8
     for (int r = 0; r < kTile / 32; ++r) {
         const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) tile-local position of the minimizer
         const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
         uint32_t lo;
         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
-        store_code(o + r * 32, make_uint2(lo, hi));
+        __stcs(o + r * 32, make_uint2(lo, hi));
     }
 }
 
@@ -314,7 +308,7 @@ __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const
 // whether starts without a code (contig seams) must be skipped and the output index compacted;
 // k-mers of colliding minimizers are flagged in s_fbmask; kChunked (more than kCap minimizers):
 // entries outside [i0, i1) are left to their own chunk.
-template <bool kChunked>
+template <int kTile, bool kChunked>
 __device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
                                              const uint8_t* s_pos, const uint8_t* s_ref,
                                              const uint32_t* s_minmask, const uint16_t* s_wpre,
@@ -346,16 +340,17 @@ __device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
         }
         const uint64_t B = (uint64_t(s_hi[idx]) << 32) | e.lo;
         const uint64_t code = B + uint64_t(int64_t(e.ns) * int64_t(q));
-        store_code(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), code);
+        __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), code);
     }
 }
 
 template <int K, int M>
-__global__ void __launch_bounds__(kThreads, LPHB_MINB)
+__global__ void __launch_bounds__(kThreads, (Cfg<K, M>::E == 1 ? LPHB_MINB : 4))
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
     constexpr int W = C::W, NW = C::NW, NH = C::NH;
+    constexpr int kTile = C::Tile, kStrip = C::Strip, kLanes = C::Lanes, kMaskWords = C::MaskWords;
 
     // dynamic shared memory: one private region per warp, tile-local coordinates
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -405,8 +400,8 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         rec.clean = v.w;
     }
     const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
-    uint32_t keymask;  // ~31 held in a register so that (hash & ~31) | position is one LOP3
-    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(keymask));
+    uint32_t keymask;  // ~position mask held in a register so that (hash & mask) | position is one LOP3
+    asm volatile("mov.u32 %0, %1;" : "=r"(keymask) : "n"(~((1u << C::PosBits) - 1u)));
 
     uint32_t iter = 0;
 #pragma unroll 1
@@ -519,9 +514,9 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
 #pragma unroll
             for (int j = 0; j < NW; ++j) wds[j] = s_packed[(lseg >> 4) + j];
 
-            // keys: top 27 bits of the m-mer's hash | thread-local position (own: 0..15, the W-1
-            // received from lane+1: 16..)
-            uint32_t key[NH];
+            // keys: top bits of the m-mer's hash | thread-local position (PosBits low bits)
+            constexpr uint32_t kPosMask = (1u << C::PosBits) - 1u;
+            uint32_t key[C::E == 1 ? NH : kS];
 #pragma unroll
             for (int j = 0; j < kS; ++j) {
                 uint32_t v_lo, v_hi;
@@ -542,42 +537,99 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                 h = mul_murmur(h);
                 asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
             }
-#pragma unroll
-            for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
 
-            uint32_t mn[kS];
-            window_min<W, NH>(key, mn);
-            // same windows with the position bits complemented: the minimum is now the RIGHTMOST one
-            // among equal 27-bit keys; both agree on every window <=> no two candidates tied
-            uint32_t agree = 31u;
-            {
+            uint32_t mn[kS];         // per k-mer: key of its minimizer (leftmost among equal key prefixes)
+            uint32_t agree = kPosMask;  // stays kPosMask <=> no window had two candidates with one prefix
+            if constexpr (C::E == 1) {
+                // W <= 17: the W-1 keys a thread lacks come from lane+1 (positions 16..); sliding
+                // minimum by sparse table
+#pragma unroll
+                for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
+                window_min<W, NH>(key, mn);
+                // same windows with the position bits complemented: the minimum is now the RIGHTMOST
+                // one among equal prefixes; both agree on every window <=> no two candidates tied
                 uint32_t rkey[NH], rmn[kS];
 #pragma unroll
-                for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ 31u;
+                for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ kPosMask;
                 window_min<W, NH>(rkey, rmn);
 #pragma unroll
                 for (int i = 0; i < kS; ++i) agree &= mn[i] ^ rmn[i];
-            }
-            if (lane < kLanes) {  // lane 31 only feeds keys to lane 30
-                uint32_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
-                if (agree == 31u) {
-                    uint32_t pk[4];
+            } else {
+                // wide windows (up to 3 lanes to the right): a window = suffix of my 16 keys, whole
+                // 16-key blocks of the next lanes, prefix of one more lane's block.  Prefix/suffix
+                // minima are thread-local; a neighbour's value arrives by shuffle and its position
+                // field is rebased by 16 per lane.  r* = same with complemented positions (rightmost).
+                uint32_t P[kS], S[kS], rP[kS], rS[kS];
+                P[0] = key[0];
+                rP[0] = key[0] ^ kPosMask;
 #pragma unroll
-                    for (int i = 0; i < kS; ++i) marks |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+                for (int j = 1; j < kS; ++j) {
+                    P[j] = min(P[j - 1], key[j]);
+                    rP[j] = min(rP[j - 1], key[j] ^ kPosMask);
+                }
+                S[kS - 1] = key[kS - 1];
+                rS[kS - 1] = key[kS - 1] ^ kPosMask;
+#pragma unroll
+                for (int j = kS - 2; j >= 0; --j) {
+                    S[j] = min(key[j], S[j + 1]);
+                    rS[j] = min(key[j] ^ kPosMask, rS[j + 1]);
+                }
+                uint32_t Bm[C::E], rBm[C::E];  // whole blocks of lanes +1 .. +E-1
+#pragma unroll
+                for (int d = 1; d < C::E; ++d) {
+                    Bm[d] = __shfl_down_sync(0xFFFFFFFFu, P[kS - 1], d) + 16u * d;
+                    rBm[d] = __shfl_down_sync(0xFFFFFFFFu, rP[kS - 1], d) - 16u * d;
+                }
+#pragma unroll
+                for (int i = 0; i < kS; ++i) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int end = i + W - 1, e = end >> 4, c = end & 15;  // compile-time after unrolling
+                    uint32_t acc = min(S[i], __shfl_down_sync(0xFFFFFFFFu, P[c], e) + 16u * e);
+                    uint32_t racc = min(rS[i], __shfl_down_sync(0xFFFFFFFFu, rP[c], e) - 16u * e);
+#pragma unroll
+                    for (int d = 1; d < C::E; ++d) {
+                        if (d < e) {
+                            acc = min(acc, Bm[d]);
+                            racc = min(racc, rBm[d]);
+                        }
+                    }
+                    mn[i] = acc;
+                    agree &= acc ^ racc;
+                }
+            }
+            if (lane < kLanes) {  // the last E lanes only feed their neighbours
+                uint64_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
+                if (agree == kPosMask) {
+                    uint32_t pk[4];
+                    if constexpr (C::E == 1) {
+                        uint32_t m32 = 0;
+#pragma unroll
+                        for (int i = 0; i < kS; ++i) m32 |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+                        marks = m32;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kS; ++i) marks |= uint64_t(1) << (mn[i] & kPosMask);
+                    }
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
                         uint32_t t0 = __byte_perm(mn[4 * g4], mn[4 * g4 + 1], 0x0040);
                         uint32_t t1 = __byte_perm(mn[4 * g4 + 2], mn[4 * g4 + 3], 0x0040);
-                        pk[g4] = __byte_perm(t0, t1, 0x5410) & 0x1F1F1F1Fu;
+                        pk[g4] = __byte_perm(t0, t1, 0x5410) & (kPosMask * 0x01010101u);
                     }
                     *reinterpret_cast<uint4*>(s_pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 } else {
                     marks = exact_strip<K, M>(s_packed, lseg, f.mm_seed, s_pos + lseg);
                 }
-                // lseg is a multiple of 16: the 32 local positions straddle at most two mask words
+                // lseg is a multiple of 16: the (up to 64) local positions straddle up to three mask words
                 const int sh = lseg & 16;
-                atomicOr(&s_minmask[lseg >> 5], marks << sh);
-                if (sh && (marks >> 16)) atomicOr(&s_minmask[(lseg >> 5) + 1], marks >> 16);
+                const uint32_t m0 = uint32_t(marks << sh), m1 = uint32_t(marks >> (32 - sh));
+                atomicOr(&s_minmask[lseg >> 5], m0);
+                if (m1) atomicOr(&s_minmask[(lseg >> 5) + 1], m1);
+                if constexpr (C::E > 1) {
+                    const uint32_t m2 = sh ? uint32_t(marks >> 48) : 0u;
+                    if (m2) atomicOr(&s_minmask[(lseg >> 5) + 2], m2);
+                }
             }
         }
         __syncwarp();
@@ -682,9 +734,9 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             special |= have && hi0 != hi_warp;
             const bool plain = !chunked && !tile_has_invalid && !__any_sync(0xFFFFFFFFu, special);
             __syncwarp();
-            if (plain) emit_plain<8>(lane, s_pos, s_ref, s_ent, hi_warp, out);
-            else if (!chunked) emit_general<false>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
-            else emit_general<true>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
+            if (plain) emit_plain<kTile>(lane, s_pos, s_ref, s_ent, hi_warp, out);
+            else if (!chunked) emit_general<kTile, false>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
+            else emit_general<kTile, true>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
             __syncwarp();
 
             // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
@@ -722,639 +774,10 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     }  // tiles of this warp
 }
 
-// =================================================================================================
-// Pipelined form of the kernel above (the default).  Same tiles, same phases A-E, same results; the
-// two dependent image gathers of phase D no longer stall the warp.  They are issued as asynchronous
-// copies (cp.async, global -> shared, no destination register) and consumed one pipeline step later,
-// with the ALU-heavy phases of the neighbouring tiles in between:
-//
-//   iteration i:   A B C (i)             pack, scan, rank                      [entry gathers of i-1 in flight]
-//                  D0 (i)                minimizer hashes -> s_h, issue the pilot gathers of tile i
-//                  D2 + E (i-1)          wait entry gathers (i-1): decode, emit [pilot gathers of i in flight]
-//                  D1 (i)                wait pilot gathers (i): table slots, issue the entry gathers of i
-//
-// What a tile needs from its scan until its emit one iteration later (minimizer offsets, list, masks,
-// packed bases) is double-buffered per warp; gather landing zones are double-buffered as well and the
-// decoded entries overwrite the landed words in place.  Tiles with more than kCap minimizers (rare)
-// drain the pipeline and run their chunks back to back.
-namespace pipe {
-constexpr int kOffLand = 0;                              // 2 x u64[kCap]: landing zone -> Entry[kCap]
-constexpr int kOffH = kOffLand + 2 * kCap * 8;           // u64[kCap] minimizer hashes (D0 -> D1)
-constexpr int kOffRef = kOffH + kCap * 8;                // u8[kSlots] position -> list index
-constexpr int kOffFb = kOffRef + kSlots;                 // u32[32] fallback k-mers
-constexpr int kOffTile = kOffFb + 128;                   // 2 x per-tile block
-constexpr int kTPos = 0;                                 // u8[kSlots]
-constexpr int kTList = kTPos + kSlots;                   // u16[kCap]
-constexpr int kTMin = kTList + kCap * 2;                 // u32[32]
-constexpr int kTInv = kTMin + 128;                       // u32[32]
-constexpr int kTWpre = kTInv + 128;                      // u16[32]
-constexpr int kTInvPre = kTWpre + 64;                    // u16[32]
-constexpr int kTPacked = kTInvPre + 64;                  // u32[kPackedSlots]
-constexpr int kTileBytes = (kTPacked + kPackedSlots * 4 + 15) / 16 * 16;
-constexpr int kOffRaw = kOffTile + 2 * kTileBytes;       // kRawBytes (TMA destination; refilled right after the pack)
-constexpr int kOffBar = kOffRaw + kRawBytes;             // mbarrier
-constexpr int kWarpBytes = kOffBar + 16;
-constexpr int kSmemBytes = kWarps * kWarpBytes;
-#ifndef LPHB_PIPE_MINB
-#define LPHB_PIPE_MINB 5
-#endif
-#ifndef LPHB_PIPE_UNROLL
-#define LPHB_PIPE_UNROLL 2
-#endif
-constexpr int kU = LPHB_PIPE_UNROLL;                     // probes a lane works on at once
-static_assert(kWarpBytes % 16 == 0 && kOffRaw % 16 == 0 && kOffTile % 16 == 0 && kTList % 2 == 0, "per-warp layout");
-
-__device__ __forceinline__ void cp_async8(void* dst, const void* src, uint64_t pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, uint64_t pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// what one warp keeps of a tile (all pointers into its own shared memory)
-struct TileSm {
-    uint8_t* pos;        // per k-mer: thread-local minimizer position
-    uint16_t* list;      // minimizer positions of the chunk
-    uint32_t* minmask;   // bit p: position p is some k-mer's minimizer
-    uint32_t* invalid;   // bit q: k-mer start q produces no code
-    uint16_t* wpre;      // marked positions before mask word
-    uint16_t* invpre;    // invalid starts before mask word
-    uint32_t* packed;    // 2-bit bases
-    uint64_t* land;      // gather landing zone, then Entry[kCap]
-};
-__device__ __forceinline__ TileSm tile_sm(unsigned char* mine, uint32_t buf) {
-    unsigned char* t = mine + kOffTile + buf * kTileBytes;
-    TileSm s;
-    s.pos = t + kTPos;
-    s.list = reinterpret_cast<uint16_t*>(t + kTList);
-    s.minmask = reinterpret_cast<uint32_t*>(t + kTMin);
-    s.invalid = reinterpret_cast<uint32_t*>(t + kTInv);
-    s.wpre = reinterpret_cast<uint16_t*>(t + kTWpre);
-    s.invpre = reinterpret_cast<uint16_t*>(t + kTInvPre);
-    s.packed = reinterpret_cast<uint32_t*>(t + kTPacked);
-    s.land = reinterpret_cast<uint64_t*>(mine + kOffLand) + buf * kCap;
-    return s;
-}
-
-// list of the marked positions with rank in [i0, i1): lane l owns mask word l
-__device__ __forceinline__ void build_list(TileSm const& t, int lane, uint32_t i0, uint32_t i1) {
-    uint32_t word = t.minmask[lane], idx = t.wpre[lane];
-    while (word) {
-        const int bit = __ffs(word) - 1;
-        word &= word - 1;
-        if (idx >= i0 && idx < i1) t.list[idx - i0] = uint16_t(lane * 32 + bit);
-        ++idx;
-    }
-    __syncwarp();
-}
-
-// The stage loops below are written phase by phase over kU probes per lane (all loads, then all
-// arithmetic, then all stores / copies), so that the independent chains of the probes interleave;
-// the copy instructions carry no memory clobber (their order against ordinary shared-memory
-// accesses is fixed by data dependences and by the clobbering commit / wait).
-__device__ __forceinline__ void cp_async8_nc(uint32_t dst, const void* src, uint64_t pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol));
-}
-__device__ __forceinline__ void cp_async4_nc(uint32_t dst, const void* src, uint64_t pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "l"(pol));
-}
-
-// D0: minimizer -> hash -> PTHash bucket; the hashed pilot is gathered asynchronously
-template <int M>
-__device__ __forceinline__ void issue_pilots(DevImage const& f, TileSm const& t, uint64_t* s_h, int lane,
-                                             uint32_t n_chunk, uint64_t keep) {
-    const DevPhf& P = f.minimizer_order;
-    const uint32_t land0 = smem_u32(t.land);
-#pragma unroll 1
-    for (uint32_t g0 = 0; g0 < n_chunk; g0 += 32 * kU) {
-        uint64_t v[kU], h[kU];
-        uint32_t slot[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const uint32_t li = g0 + 32 * u + lane;
-            v[u] = mmer_at<M>(t.packed, t.list[li < n_chunk ? li : 0]);  // dead lanes redo entry 0 (unused)
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            h[u] = murmur64(v[u], P.seed);
-            slot[u] = phf_bucket(P, h[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const uint32_t li = g0 + 32 * u + lane;
-            if (li < n_chunk) {
-                s_h[li] = h[u];
-#ifdef LPHB_EXP_LOCALGATHER  // timing experiment only (wrong codes): gathers confined to 8 KB
-                cp_async8_nc(land0 + li * 8, P.pilot_hash + (slot[u] & 1023u), keep);
-#else
-                cp_async8_nc(land0 + li * 8, P.pilot_hash + slot[u], keep);
-#endif
-            }
-        }
-    }
-    cp_async_commit();
-}
-
-// D1: hashed pilot landed -> table slot; the bucket word is gathered asynchronously into the same slot
-__device__ __forceinline__ void issue_entries(DevImage const& f, TileSm const& t, const uint64_t* s_h, int lane,
-                                              uint32_t n_chunk, uint64_t keep) {
-    const DevPhf& P = f.minimizer_order;
-    const uint32_t land0 = smem_u32(t.land);
-#pragma unroll 1
-    for (uint32_t g0 = 0; g0 < n_chunk; g0 += 32 * kU) {
-        uint64_t x[kU];
-        uint32_t ts[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const uint32_t li = g0 + 32 * u + lane;
-            const uint32_t lj = li < n_chunk ? li : 0;
-            x[u] = s_h[lj] ^ t.land[lj];
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) ts[u] = phf_table_slot(P, x[u]);
-        // indexed by the raw table slot (free slots folded in at load time)
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const uint32_t li = g0 + 32 * u + lane;
-            if (li < n_chunk) {
-#ifdef LPHB_EXP_LOCALGATHER
-                ts[u] &= 2047u;
-#endif
-                if (f.buckets.wide) cp_async8_nc(land0 + li * 8, reinterpret_cast<const uint64_t*>(f.buckets.entries) + ts[u], keep);
-                else cp_async4_nc(land0 + li * 8, reinterpret_cast<const uint32_t*>(f.buckets.entries) + ts[u], keep);
-            }
-        }
-    }
-    cp_async_commit();
-}
-
-struct Pending {      // a tile between its D1 and its emit
-    uint64_t* out;
-    uint32_t n_min;
-    uint32_t buf;
-    bool live;
-    bool has_invalid;
-};
-
-// Pipelined-kernel entries: x = low word of B, y = ns + 4 * (high word of B) (ns in {-1, 0, +1},
-// B < 2^62), so that a tile whose codes stay below 2^32 reads y as the slope directly.
-//
-// General emit (tiles with contig seams, colliding minimizers, high words, or several chunks): per
-// group of 32 starts the (warp-uniform) word of the invalid-start mask tells which starts have no
-// code; the output index is compacted accordingly.  k-mers of colliding minimizers are flagged in
-// s_fbmask.  kChunked: entries outside [i0, i1) are left to their own chunk.
-template <bool kChunked>
-__device__ __forceinline__ void emit_general_p(int lane, uint32_t i0, uint32_t i1, TileSm const& t,
-                                               const uint8_t* s_ref, const Entry* s_ent,
-                                               uint32_t* s_fbmask, uint64_t* out) {
-    const int lane16 = lane & 16;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint64_t* out_l = out + lane;
-#pragma unroll 2
-    for (int r = 0; r < kTile / 32; ++r) {
-        const int q = lane + r * 32;
-        const uint32_t mw = t.invalid[r];  // uniform in the warp
-        const int mp = int(t.pos[q]) + lane16 + r * 32;  // tile-local position of q's minimizer
-        uint32_t idx;
-        bool live = !((mw >> lane) & 1u);
-        if (kChunked) {  // global list index of position mp: rank among the marked positions
-            idx = t.wpre[mp >> 5] + __popc(t.minmask[mp >> 5] & ((1u << (mp & 31)) - 1u));
-            live = live && idx >= i0 && idx < i1;
-            idx = live ? idx - i0 : 0u;
-        } else {
-            idx = s_ref[mp];
-        }
-        const int2 e = *reinterpret_cast<const int2*>(s_ent + (live ? idx : 0u));
-        const int32_t ns = int32_t((uint32_t(e.y) + 1u) & 3u) - 1;
-        const uint32_t hi = uint32_t(e.y - ns) >> 2;
-        const uint64_t B = (uint64_t(hi) << 32) | uint32_t(e.x);
-        const uint64_t code = B + uint64_t(int64_t(ns) * int64_t(q));
-        if (live) {
-            if (ns != 0) store_code(out_l + (r * 32 - int(t.invpre[r]) - __popc(mw & lt)), code);
-            else atomicOr(&s_fbmask[r], 1u << lane);  // colliding minimizer: needs the k-mer itself (rare)
-        }
-    }
-}
-
-// Colliding minimizers: every k-mer of the run goes through fallback_kmer_order
-// (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134).  Lane l takes bit l of every mask
-// word, so the consecutive k-mers of a run spread over the lanes and their (dependent, uncached)
-// gathers overlap.  Rare: out of line, away from the hot loop's instruction-cache footprint.
-template <int K, int M>
-static __device__ __noinline__ void fallback_kmers(DevImage const& f, TileSm const& t, uint32_t* s_fbmask,
-                                                   int lane, uint64_t* out) {
-    constexpr int NW = Cfg<K, M>::NW;
-#pragma unroll 1
-    for (int r = 0; r < kMaskWords; ++r) {
-        const uint32_t fw = s_fbmask[r];  // uniform
-        if (!((fw >> lane) & 1u)) continue;
-        const int g = r * 32 + lane;
-        const int wi = g >> 4, sh2 = (g & 15) * 2;
-        uint32_t x[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? t.packed[min(wi + j, kPackedSlots - 1)] : 0u;
-        uint32_t y[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], sh2);
-        // y[0..3] = 128-bit window starting at base g (y[0] most significant)
-        uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
-        uint64_t klo, khi;
-        if constexpr (K <= 32) {
-            klo = top >> (64 - 2 * K);
-            khi = 0;
-            (void)bot;
-        } else {
-            constexpr int sh = 128 - 2 * K;  // 2..62
-            klo = (bot >> sh) | (top << (64 - sh));
-            khi = top >> sh;
-        }
-        const uint32_t mw = t.invalid[r];
-        const int oidx = g - int(t.invpre[r] + __popc(mw & ((1u << lane) - 1u)));
-        out[oidx] = fallback_code(f, klo, khi);
-    }
-    __syncwarp();
-    if (lane < kMaskWords) s_fbmask[lane] = 0;
-    __syncwarp();
-}
-
-// D2 + E of one chunk [i0, i1) of a tile whose bucket words have landed.  kChunked = false is the
-// hot-loop copy (one chunk per tile); loops are kept rolled (kD probes per lane at a time): the hot
-// loop must stay well inside the 32 KB instruction cache.
-template <int K, int M, bool kChunked>
-__device__ __forceinline__ void finish_chunk(DevImage const& f, TileSm const& t, unsigned char* mine, int lane,
-                                             uint32_t i0, uint32_t i1, bool has_invalid, uint64_t* out) {
-    constexpr int kD = 2;
-    Entry* s_ent = reinterpret_cast<Entry*>(t.land);
-    uint8_t* s_ref = mine + kOffRef;
-    uint32_t* s_fbmask = reinterpret_cast<uint32_t*>(mine + kOffFb);
-    const uint32_t n_chunk = i1 - i0;
-    const int fsh = f.buckets.wide ? 62 : 30;
-    const uint64_t bmask = (uint64_t(1) << fsh) - 1;
-    bool special = false;
-    // bucket word -> {B, ns}: hval = base + slope * (bp - q) = (base + slope * bp) + (-slope) * q
-#pragma unroll 1
-    for (uint32_t g0 = 0; g0 < n_chunk; g0 += 32 * kD) {
-        uint64_t word[kD];
-        int bp[kD];
-#pragma unroll
-        for (int u = 0; u < kD; ++u) {
-            const uint32_t li = g0 + 32 * u + lane, lj = li < n_chunk ? li : 0;
-            word[u] = f.buckets.wide ? t.land[lj] : uint64_t(reinterpret_cast<const uint2*>(t.land + lj)->x);
-            bp[u] = t.list[lj];
-        }
-#pragma unroll
-        for (int u = 0; u < kD; ++u) {
-            const uint32_t li = g0 + 32 * u + lane;
-            const uint32_t flags = uint32_t(word[u] >> fsh);  // bit 1: slope +1, bit 0: colliding
-            const int32_t ns = (flags & 1u) ? 0 : ((flags & 2u) ? -1 : 1);
-            const uint64_t B = (word[u] & bmask) - uint64_t(int64_t(ns) * bp[u]);
-            const uint32_t lo = uint32_t(B), hi = uint32_t(B >> 32);
-            if (li < n_chunk) {  // own slot: read above, rewritten in place
-                special |= ns == 0 || hi != 0 || lo - 1024u >= 0xFFFFF800u;  // needs 64-bit care
-                s_ent[li] = Entry{lo, ns + int32_t(hi << 2)};
-                s_ref[bp[u]] = uint8_t(li);
-            }
-        }
-    }
-    // plain emit needs: codes below 2^32 that cannot carry, no colliding minimizer, no start
-    // without a code, one chunk
-    const bool plain = !kChunked && !has_invalid && !__any_sync(0xFFFFFFFFu, special);
-    __syncwarp();
-    if (plain) {
-        emit_plain<4>(lane, t.pos, s_ref, s_ent, 0u, out);
-        __syncwarp();
-        return;
-    }
-    emit_general_p<kChunked>(lane, i0, i1, t, s_ref, s_ent, s_fbmask, out);
-    __syncwarp();
-    const uint32_t fb_any = lane < kMaskWords ? s_fbmask[lane] : 0u;
-    if (__any_sync(0xFFFFFFFFu, fb_any != 0)) fallback_kmers<K, M>(f, t, s_fbmask, lane, out);
-}
-
-// A tile with more minimizers than one chunk holds (rare): chunk by chunk, nothing in flight across
-// chunks.  Out of line.
-template <int K, int M>
-static __device__ __noinline__ void slow_tile(DevImage const& f, TileSm const& t, unsigned char* mine, int lane,
-                                              uint32_t n_min, bool has_invalid, uint64_t* out, uint64_t keep) {
-    uint64_t* s_h = reinterpret_cast<uint64_t*>(mine + kOffH);
-    for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
-        const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
-        build_list(t, lane, i0, i1);
-        issue_pilots<M>(f, t, s_h, lane, i1 - i0, keep);
-        cp_async_wait<0>();
-        issue_entries(f, t, s_h, lane, i1 - i0, keep);
-        cp_async_wait<0>();
-        finish_chunk<K, M, true>(f, t, mine, lane, i0, i1, has_invalid, out);
-    }
-}
-
-// k-mer starts of a tile that produce no code (contig seams, short contigs, positions outside
-// [first, end)) -> t.invalid.  Only for tiles that one contig does not cover: out of line.
-template <int K>
-static __device__ __noinline__ void mark_invalid(DevBatch const& b, TileSm const& t, int lane, int64_t T0,
-                                                 uint32_t c0) {
-    const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
-    const int64_t tile_end = T0 + kTile;
-    if (T0 < first) {  // head padding of the first tile (< 16 positions)
-        int n = int(first - T0);
-        if (lane == 0) atomicOr(&t.invalid[0], (1u << n) - 1u);
-    }
-    uint64_t c = c0;
-    for (;; c += 32) {
-        uint64_t cc = c + lane;
-        bool live = cc < b.n_contigs;
-        int64_t s = live ? int64_t(__ldg(b.offsets + cc)) : end;
-        int64_t e = live ? int64_t(__ldg(b.offsets + cc + 1)) : end;
-        if (live && s < tile_end) {
-            // starts in [max(e-K+1, s), e) have fewer than K bases left in their contig
-            int64_t lo = e - (K - 1) > s ? e - (K - 1) : s;
-            int64_t hi = e;
-            if (lo < T0) lo = T0;
-            if (hi > tile_end) hi = tile_end;
-            for (int64_t q = lo; q < hi;) {
-                int ql = int(q - T0);
-                int wbit = ql & 31;
-                int n = int(hi - q) < 32 - wbit ? int(hi - q) : 32 - wbit;
-                uint32_t bits = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << wbit;
-                atomicOr(&t.invalid[ql >> 5], bits);
-                q += n;
-            }
-        }
-        // go on while the contig after lane 31's also starts inside the tile
-        if (!__any_sync(0xFFFFFFFFu, lane == 31 && live && e < tile_end)) break;
-    }
-    if (end < tile_end) {  // past the last base of the batch
-        int lo = end > T0 ? int(end - T0) : 0;
-        if (lane >= (lo >> 5) && lane < kMaskWords) {
-            uint32_t bits = 0xFFFFFFFFu;
-            if (lane == (lo >> 5)) bits <<= (lo & 31);
-            atomicOr(&t.invalid[lane], bits);
-        }
-    }
-    __syncwarp();
-}
-}  // namespace pipe
-
-template <int K, int M>
-__global__ void __launch_bounds__(kThreads, LPHB_PIPE_MINB)
-k_query_pipe(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
-             const __grid_constant__ TileArgs a) {
-    using C = Cfg<K, M>;
-    using namespace pipe;
-    constexpr int W = C::W, NW = C::NW, NH = C::NH;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* mine = smem_raw + warp * pipe::kWarpBytes;
-    uint64_t* s_h = reinterpret_cast<uint64_t*>(mine + pipe::kOffH);
-    unsigned char* s_rawbuf = mine + pipe::kOffRaw;
-    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(mine + pipe::kOffBar);
-
-    const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
-    const uint32_t n_warps = gridDim.x * kWarps;
-    uint32_t tile = blockIdx.x * kWarps + warp;
-    auto tile_bytes = [&](uint32_t t) -> uint32_t {
-        const int64_t t0 = a.pos0 + int64_t(t) * kTile;
-        int64_t words = (end - t0 + 15) >> 4;
-        if (words > C::TileWords) words = C::TileWords;
-        return uint32_t(words) * 16u;
-    };
-    const uint64_t stream_pol = l2_stream_policy();
-    const uint64_t keep = l2_keep_policy();
-    reinterpret_cast<uint32_t*>(mine + pipe::kOffFb)[lane] = 0;
-#ifdef LPHB_RAW_TMA
-    if (lane == 0) {
-        mbar_init(&s_mbar[0], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (tile < a.n_tiles) {
-            const uint32_t nb = tile_bytes(tile);
-            mbar_expect_tx(&s_mbar[0], nb);
-            tma_load_1d(s_rawbuf, a.abase + int64_t(tile) * kTile, nb, &s_mbar[0], stream_pol);
-        }
-    }
-#else
-    // raw bytes of a tile: 16-byte asynchronous copies, one group per tile; every later wait in the
-    // loop also covers it (groups complete in order)
-    auto load_raw = [&](uint32_t tl) {
-        const int nw = int(tile_bytes(tl) >> 4);
-        const char* src = a.abase + int64_t(tl) * kTile;
-#pragma unroll 1
-        for (int w = lane; w < nw; w += 32) cp_async16(s_rawbuf + w * 16, src + w * 16, stream_pol);
-        cp_async_commit();
-    };
-    if (tile < a.n_tiles) load_raw(tile);
-    cp_async_wait<0>();
-    (void)s_mbar;
-#endif
-    __syncwarp();
-    TileRec rec{};
-    if (tile < a.n_tiles) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.recs + tile));
-        rec.out = (uint64_t(v.y) << 32) | v.x;
-        rec.c0 = v.z;
-        rec.clean = v.w;
-    }
-    const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
-    uint32_t keymask;  // ~31 held in a register so that (hash & ~31) | position is one LOP3
-    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(keymask));
-
-    // One more trip than the warp has tiles: the last one only drains the pipeline, so that every
-    // stage has exactly one copy of its code (the loop body must fit the instruction cache).
-    Pending prev{};
-    uint32_t iter = 0;
-#pragma unroll 1
-    for (;; tile += n_warps, ++iter) {
-        const bool have_tile = tile < a.n_tiles;
-        if (!have_tile && !prev.live) break;
-        const uint32_t buf = iter & 1u;
-        const TileSm t = tile_sm(mine, buf);
-        uint32_t n_min = 0;
-        bool tile_has_invalid = false, one_chunk = false;
-        uint64_t* out = nullptr;
-        if (have_tile) {
-            const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
-            const TileRec cur = rec;
-
-            // -------------------------------------------------------- A: stage + pack ------------
-            const uint32_t next = tile + n_warps;
-            if (next < a.n_tiles) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.recs + next));
-                rec.out = (uint64_t(v.y) << 32) | v.x;
-                rec.c0 = v.z;
-                rec.clean = v.w;
-            }
-            t.minmask[lane] = 0;
-            t.invalid[lane] = 0;
-#ifdef LPHB_RAW_TMA
-            mbar_wait(&s_mbar[0], iter & 1u);
-#endif
-            const int n_words = int(tile_bytes(tile) >> 4);
-#pragma unroll 1
-            for (int w = lane; w < kPackedSlots; w += 32) {
-                uint32_t word = 0;
-                if (w < n_words) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(s_rawbuf + w * 16);
-                    uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
-                    word = (pack4(y0) << 24) | (pack4(y1) << 16) | (pack4(y2) << 8) | pack4(y3);
-                    uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
-                    if (bad) mark_dirty(b, v, T0 + int64_t(w) * 16);  // rare
-                }
-                t.packed[w] = word;
-            }
-            __syncwarp();
-            // the raw bytes are consumed: refill the buffer with this warp's next tile, which then has
-            // the rest of the iteration to arrive
-#ifdef LPHB_RAW_TMA
-            if (next < a.n_tiles && lane == 0) {
-                const uint32_t nb = tile_bytes(next);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&s_mbar[0], nb);
-                tma_load_1d(s_rawbuf, a.abase + int64_t(next) * kTile, nb, &s_mbar[0], stream_pol);
-            }
-#else
-            if (next < a.n_tiles) load_raw(next);
-#endif
-
-            const bool tile_clean = cur.clean != 0;
-            if (!tile_clean) mark_invalid<K>(b, t, lane, T0, cur.c0);
-            {   // exclusive prefix of invalid counts per mask word (one word per lane)
-                const uint32_t mw = tile_clean ? 0u : t.invalid[lane];
-                tile_has_invalid = __any_sync(0xFFFFFFFFu, mw != 0 && lane < kMaskWords);
-                uint32_t cnt = __popc(mw), inc = cnt;
-                if (tile_has_invalid) {
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                        if (lane >= o) inc += v;
-                    }
-                }
-                t.invpre[lane] = uint16_t(inc - cnt);
-            }
-
-            // -------------------------------------------------------- B: per-thread scan --------
-#pragma unroll 1
-            for (int strip = 0; strip < kStrips; ++strip) {
-                const int lseg = strip * kStrip + lane * kS;
-                uint32_t wds[NW];
-#pragma unroll
-                for (int j = 0; j < NW; ++j) wds[j] = t.packed[(lseg >> 4) + j];
-                uint32_t key[NH];
-#pragma unroll
-                for (int j = 0; j < kS; ++j) {
-                    uint32_t v_lo, v_hi;
-                    if constexpr (M <= 16) {
-                        v_lo = M == 16 ? win16<NW>(wds, j) : win16<NW>(wds, j) >> (32 - 2 * M);
-                        v_hi = 0;
-                    } else {
-                        v_lo = win16<NW>(wds, j + M - 16);
-                        v_hi = win16<NW>(wds, j) >> (64 - 2 * M);
-                    }
-#ifdef LPHB_EXP_SKIP_HASH  // timing experiment only (wrong codes)
-                    uint64_t h = (uint64_t(v_lo * 0x9E3779B1u) << 32) ^ h0 ^ v_hi;
-#else
-                    // MurmurHash2-64 up to its last multiply: the final h ^= h >> 47 cannot change
-                    // the top 32 bits
-                    uint64_t x = M <= 16 ? uint64_t(v_lo) * kMurmurM : mul_murmur(v_lo, v_hi);
-                    x ^= x >> 47;
-                    x = mul_murmur(x);
-                    uint64_t h = mul_murmur(h0 ^ x);
-                    h ^= h >> 47;
-                    h = mul_murmur(h);
-#endif
-                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
-                }
-#pragma unroll
-                for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
-
-                uint32_t mn[kS];
-                window_min<W, NH>(key, mn);
-                // same windows with the position bits complemented: the minimum is now the RIGHTMOST
-                // one among equal 27-bit keys; both agree on every window <=> no two candidates tied
-                uint32_t agree = 31u;
-                {
-                    uint32_t rkey[NH], rmn[kS];
-#pragma unroll
-                    for (int j = 0; j < NH; ++j) rkey[j] = key[j] ^ 31u;
-                    window_min<W, NH>(rkey, rmn);
-#pragma unroll
-                    for (int i = 0; i < kS; ++i) agree &= mn[i] ^ rmn[i];
-                }
-                if (lane < kLanes) {  // lane 31 only feeds keys to lane 30
-                    uint32_t marks = 0;
-                    if (agree == 31u) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < kS; ++i) marks |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            uint32_t t0 = __byte_perm(mn[4 * g4], mn[4 * g4 + 1], 0x0040);
-                            uint32_t t1 = __byte_perm(mn[4 * g4 + 2], mn[4 * g4 + 3], 0x0040);
-                            pk[g4] = __byte_perm(t0, t1, 0x5410) & 0x1F1F1F1Fu;
-                        }
-                        *reinterpret_cast<uint4*>(t.pos + lseg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    } else {
-                        marks = exact_strip<K, M>(t.packed, lseg, f.mm_seed, t.pos + lseg);
-                    }
-                    const int sh = lseg & 16;
-                    atomicOr(&t.minmask[lseg >> 5], marks << sh);
-                    if (sh && (marks >> 16)) atomicOr(&t.minmask[(lseg >> 5) + 1], marks >> 16);
-                }
-            }
-            __syncwarp();
-
-            // -------------------------------------------------------- C: rank the minimizers ----
-            {
-                const uint32_t n_mine = __popc(t.minmask[lane]);
-                uint32_t inc = n_mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                t.wpre[lane] = uint16_t(inc - n_mine);
-            }
-            out = b.codes + cur.out;
-
-            // -------------------------------------------------------- D0 ---------------------------
-            one_chunk = n_min <= kCap;
-            if (one_chunk) {
-                build_list(t, lane, 0, n_min);
-                issue_pilots<M>(f, t, s_h, lane, n_min, keep);
-            }
-        }
-        // ------------------------------------------------------------ D2 + E of the previous tile --
-        if (prev.live) {
-            if (one_chunk) cp_async_wait<1>();  // everything but the pilot gathers just issued
-            else cp_async_wait<0>();
-            finish_chunk<K, M, false>(f, tile_sm(mine, prev.buf), mine, lane, 0, prev.n_min, prev.has_invalid, prev.out);
-            prev.live = false;
-        }
-        // ------------------------------------------------------------ D1 ---------------------------
-        if (one_chunk) {
-            cp_async_wait<0>();
-            issue_entries(f, t, s_h, lane, n_min, keep);
-            prev.out = out;
-            prev.n_min = n_min;
-            prev.buf = buf;
-            prev.has_invalid = tile_has_invalid;
-            prev.live = true;
-        } else if (have_tile) {  // more minimizers than one chunk holds
-            slow_tile<K, M>(f, t, mine, lane, n_min, tile_has_invalid, out, keep);
-        }
-    }
-}
-
 // per tile: contig containing its first in-range position, number of valid k-mer starts before it,
 // and whether one contig covers the tile plus k-1 bases (then every start yields a code)
 __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, uint32_t n_tiles,
-                             uint32_t k, TileRec* recs) {
+                             uint32_t k, int kTile, TileRec* recs) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const int64_t t0 = pos0 + int64_t(t) * kTile;
@@ -1375,68 +798,45 @@ __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, u
     recs[t] = r;
 }
 
-// LPHB_QUERY_IMPL=pipe selects the pipelined kernel (A-B comparison only: it is slower)
-bool use_pipe() {
-    static const bool pipe_on = [] {
-        const char* e = getenv("LPHB_QUERY_IMPL");
-        return e && e[0] == 'p';
-    }();
-    return pipe_on;
-}
-
-// LPHB_EXP_SMEM_PAD=<bytes>: extra dynamic shared memory per CTA (occupancy experiments only)
-int smem_pad() {
-    static const int pad = [] {
-        const char* e = getenv("LPHB_EXP_SMEM_PAD");
-        return e ? atoi(e) : 0;
-    }();
-    return pad;
-}
-
-template <class Kern>
-int resident_ctas(Kern kern, int smem) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
-    return sms * (per_sm > 0 ? per_sm : 1);
-}
-
 template <int K, int M>
 void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaStream_t stream) {
-    // per instantiation (the attribute is per device function): CTAs that fit the device at once
-    const int smem_pipe = pipe::kSmemBytes + smem_pad(), smem_tiled = kSmemBytes + smem_pad();
-    static const int resident_pipe = resident_ctas(k_query_pipe<K, M>, smem_pipe);
-    static const int resident_tiled = resident_ctas(k_query_tiled<K, M>, smem_tiled);
+    static bool configured = false;  // per instantiation; the attribute is per device function
+    static int resident = 0;         // CTAs that fit the device at once
+    if (!configured) {
+        cudaFuncSetAttribute(k_query_tiled<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query_tiled<K, M>, kThreads, kSmemBytes);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+        configured = true;
+    }
     // persistent grid: every warp walks tiles (global warp id) + i * (number of warps)
-    const bool p = use_pipe();
-    const uint32_t resident = uint32_t(p ? resident_pipe : resident_tiled);
     const uint32_t ctas_needed = (a.n_tiles + kWarps - 1) / kWarps;
-    const uint32_t grid = ctas_needed < resident ? ctas_needed : resident;
-    if (p) k_query_pipe<K, M><<<grid, kThreads, smem_pipe, stream>>>(img, b, a);
-    else k_query_tiled<K, M><<<grid, kThreads, smem_tiled, stream>>>(img, b, a);
+    const uint32_t grid = ctas_needed < uint32_t(resident) ? ctas_needed : uint32_t(resident);
+    k_query_tiled<K, M><<<grid, kThreads, kSmemBytes, stream>>>(img, b, a);
 }
 
 }  // namespace
 
 uint64_t query_tiled_ws_bytes(uint64_t span_bases) {
-    uint64_t n_tiles = (span_bases + 16) / kTile + 2;
+    uint64_t n_tiles = (span_bases + 16) / kMinTile + 2;
     return n_tiles * sizeof(TileRec) + 64;
 }
 
 bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream) {
     const uint32_t k = img.k, m = img.m;
     void (*fn)(DevImage const&, DevBatch const&, TileArgs const&, cudaStream_t) = nullptr;
-    if (k == 31 && m == 20) fn = launch_cfg<31, 20>;
-    else if (k == 31 && m == 16) fn = launch_cfg<31, 16>;
-    else if (k == 31 && m == 15) fn = launch_cfg<31, 15>;
-    else if (k == 31 && m == 17) fn = launch_cfg<31, 17>;
-    else if (k == 31 && m == 18) fn = launch_cfg<31, 18>;
-    else if (k == 31 && m == 19) fn = launch_cfg<31, 19>;
-    else if (k == 31 && m == 21) fn = launch_cfg<31, 21>;
-    else if (k == 21 && m == 11) fn = launch_cfg<21, 11>;
-    else if (k == 15 && m == 7) fn = launch_cfg<15, 7>;
+    int tile = 0;  // k-mer starts per tile of the instantiation
+#define LPHB_CFG(KK, MM)                  \
+    if (k == KK && m == MM) {             \
+        fn = launch_cfg<KK, MM>;          \
+        tile = Cfg<KK, MM>::Tile;         \
+    }
+    LPHB_CFG(31, 20) LPHB_CFG(31, 16) LPHB_CFG(31, 15) LPHB_CFG(31, 17) LPHB_CFG(31, 18) LPHB_CFG(31, 19)
+    LPHB_CFG(31, 21) LPHB_CFG(21, 11) LPHB_CFG(15, 7)
+    LPHB_CFG(63, 24) LPHB_CFG(47, 20)  // wide windows (W = 40, 28), 128-bit k-mers
+#undef LPHB_CFG
     if (!fn || !b.tile_ws || b.n_contigs == 0 || b.n_contigs >= (1ull << 32)) return false;
     if (b.end_base <= b.first_base) return true;
     TileArgs a{};
@@ -1445,13 +845,13 @@ bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t str
     a.abase = p - ali;
     a.pos0 = int64_t(b.first_base) - int64_t(ali);
     uint64_t span = uint64_t(int64_t(b.end_base) - a.pos0);
-    uint64_t n_tiles = (span + kTile - 1) / kTile;
+    uint64_t n_tiles = (span + tile - 1) / tile;
     if (n_tiles >= (1ull << 31)) return false;
     a.n_tiles = uint32_t(n_tiles);
     if (query_tiled_ws_bytes(b.end_base - b.first_base) > b.tile_ws_bytes) return false;
     TileRec* recs = reinterpret_cast<TileRec*>(b.tile_ws);
     a.recs = recs;
-    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, k, recs);
+    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, k, tile, recs);
     fn(img, b, a, stream);
     return true;
 }

@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""Measurements of the SURVEY.md §8 rows that bench.py's headline line does not cover, one JSON line
+each (kept under profiles/):
+
+  scan    build-side minimizer / super-k-mer scan (lphb_scan_superkmers) over the config-2 unitigs,
+          k=31 m=20, host buffers in and out (the C ABI has no device-resident scan entry), parity
+          against the oracle on a prefix, the reference's from_string timed beside it
+  k63     BASELINE config 4: k=63 m=24, 128-bit kmer_t, streaming query of the index's own unitigs
+  reads   BASELINE config 5 shape on one GPU: 150-base reads, half of them substrings of the indexed
+          genome with 1 % substitutions, half random (mixed member / non-member k-mers), against the
+          config-2 index; parity against the oracle on a prefix
+
+    python tools/bench_rows.py [scan] [k63] [reads] [--kmers N] [--reads N]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench as B  # noqa: E402  (workload cache, log)
+
+
+def peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def build_index(tag, bases, offsets, k, m, bits):
+    from lphash_b200 import synth
+    from oracle import ref
+    os.makedirs(B.CACHE, exist_ok=True)
+    lph = os.path.join(B.CACHE, tag + ".lph")
+    if not os.path.exists(lph):
+        fa = os.path.join(B.CACHE, tag + ".fa")
+        synth.write_fasta(fa, bases, offsets)
+        t0 = time.time()
+        csv = ref.build(fa, k, m, lph + ".tmp", bits=bits, threads=min(os.cpu_count() or 1, 32), tmp_dir=B.CACHE)
+        os.replace(lph + ".tmp", lph)
+        os.remove(fa)
+        B.log(f"[rows] reference build-p {tag}: {csv} ({time.time() - t0:.1f}s)")
+    return lph
+
+
+def time_query(f, bases, offsets, k, steps=20, warmup=3):
+    """Device-resident streaming query: returns (n_codes, kernel_ms mean, ms per step, codes)."""
+    import torch
+    dev = torch.device("cuda:0")
+    n_contigs = len(offsets) - 1
+    n_kmers = int(np.maximum(np.diff(offsets).astype(np.int64) - k + 1, 0).sum())
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_codes = torch.empty(n_kmers, dtype=torch.int64, device=dev)
+    d_code_off = torch.empty(n_contigs + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step():
+        f.query_device(d_bases.data_ptr(), d_off.data_ptr(), offsets, d_codes.data_ptr(), n_kmers,
+                       d_code_off.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    st = d_status.cpu().numpy()
+    assert st[0] == n_kmers and st[1] == 0, f"unexpected status {st}"
+    f.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    kms = float(f.stats().kernel_ms)
+    codes = d_codes.cpu().numpy().view(np.uint64)
+    return n_kmers, kms, ms, codes
+
+
+def prefix_batch(bases, offsets, n_contigs):
+    n_contigs = min(n_contigs, len(offsets) - 1)
+    off = offsets[: n_contigs + 1]
+    return bases[int(off[0]): int(off[-1])], off - off[0]
+
+
+def row_query(name, workload, lph, bits, k, m, bases, offsets, members_all, oracle_contigs, steps):
+    from lphash_b200 import api
+    from oracle import oracle
+    f = api.Mphf.load(lph, bits, device=0)
+    n_kmers, kms, ms, codes = time_query(f, bases, offsets, k, steps=steps)
+    checks = []
+    if members_all:  # an all-member set: codes are a permutation of 0..n-1
+        assert len(codes) == f.get_kmer_count() and int(codes.max()) == len(codes) - 1
+        chk = np.zeros(len(codes), dtype=np.uint8)
+        chk[codes] = 1
+        assert int(chk.sum()) == len(codes), "codes are not a permutation"
+        checks.append("codes are a permutation of 0..n-1")
+    pb, po = prefix_batch(bases, offsets, oracle_contigs)
+    o = oracle.OracleMphf(lph, bits)
+    want, _ = o.query_batch(pb, po)
+    o.close()
+    assert np.array_equal(codes[: len(want)], want), "codes differ from the oracle"
+    checks.append(f"first {len(want)} codes bit-exact vs the CPU oracle")
+    # the reference's own streaming query on the host cores, bounded sample
+    cpu = None
+    try:
+        from oracle import ref
+        threads = os.cpu_count() or 1
+        r = ref.RefMphf(lph, bits)
+        sb, so = prefix_batch(bases, offsets, max(64, (len(offsets) - 1) // 4))
+        secs, n, _, _ = r.query_batch(sb, so, threads=threads, want_codes=False)
+        secs, n, _, _ = r.query_batch(sb, so, threads=threads, want_codes=False)
+        r.close()
+        cpu = {"value": n / secs, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+               "sample": f"{n} k-mers (first quarter of the contigs), one pass after one warm-up"}
+    except Exception as e:
+        cpu = {"unavailable": str(e)}
+    f.close()
+    peak, src = peak_gbs()
+    algo = int(offsets[-1] - offsets[0]) + 8 * n_kmers
+    ach = algo / (kms * 1e-3) / 1e9
+    return {"row": name, "metric": "query-p k-mers/sec", "value": n_kmers / (ms * 1e-3), "unit": "k-mers/s",
+            "n_gpus": 1, "ms_per_step": ms, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "k": k, "m": m, "kmer_bits": bits, "kmers": n_kmers},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": algo, "peak_source": src},
+            "parity": checks, "cpu_baseline": cpu}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rows", nargs="*", default=["scan", "k63", "reads"])
+    ap.add_argument("--kmers", type=int, default=100_000_000)
+    ap.add_argument("--reads", type=int, default=4_000_000)
+    ap.add_argument("--steps", type=int, default=20)
+    args = ap.parse_args()
+    from lphash_b200 import api, synth
+
+    if "scan" in args.rows:
+        from oracle import oracle
+        k, m = 31, 20
+        bases, offsets = synth.unitigs(args.kmers, k, m)
+        api.scan_superkmers(*prefix_batch(bases, offsets, 64), k, m)  # warm-up (context, module load)
+        t0 = time.perf_counter()
+        rec, nk, mm = api.scan_superkmers(bases, offsets, k, m)
+        secs = time.perf_counter() - t0
+        pb, po = prefix_batch(bases, offsets, 256)
+        wrec, wnk, wmm = oracle.scan(pb, po, k, m, mode=0)
+        assert np.array_equal(rec[: len(wrec)], wrec), "scan records differ from the oracle"
+        assert int(rec["size"].astype(np.int64).sum()) == nk, "record sizes do not add up to the k-mer count"
+        cpu = None
+        try:
+            from oracle import ref
+            sb, so = prefix_batch(bases, offsets, (len(offsets) - 1) // 8)
+            t1 = time.perf_counter()
+            out = ref.scan(sb, so, k, m, bits=64)
+            t1 = time.perf_counter() - t1
+            n_s = int(np.maximum(np.diff(so).astype(np.int64) - k + 1, 0).sum())
+            cpu = {"value": n_s / t1, "unit": "k-mers/s", "cores": 1, "kind": "reference",
+                   "sample": f"{n_s} k-mers (first eighth of the contigs), minimizer::from_string, 1 thread, "
+                             "incl. the harness's copy of the records"}
+        except Exception as e:
+            cpu = {"unavailable": str(e)}
+        peak, src = peak_gbs()
+        algo = int(offsets[-1]) + 18 * len(rec)
+        print(json.dumps({"row": "scan", "metric": "build-p scan k-mers/sec", "value": nk / secs, "unit": "k-mers/s",
+                          "n_gpus": 1, "ms_per_step": secs * 1e3, "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": "BASELINE config 2 unitigs, build-side minimizer/super-k-mer scan "
+                                                 "through lphb_scan_superkmers (host buffers in and out)",
+                                     "k": k, "m": m, "kmers": int(nk), "records": int(len(rec)), "mm_count": int(mm)},
+                          "e2e": {"value": nk / secs, "unit": "k-mers/s", "h2d_bytes_per_step": int(offsets[-1]) + 8 * len(offsets),
+                                  "d2h_bytes_per_step": 18 * len(rec)},
+                          "roofline": {"bound": "hbm", "achieved": algo / secs / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": algo / secs / 1e9 / peak, "algorithmic_bytes_per_launch": algo,
+                                       "peak_source": src, "note": "whole call incl. PCIe copies (no device-resident entry point)"},
+                          "parity": [f"first {len(wrec)} records bit-exact vs the CPU oracle", "sum of record sizes == k-mer count"],
+                          "cpu_baseline": cpu}), flush=True)
+
+    if "k63" in args.rows:
+        k, m, bits = 63, 24, 128
+        bases, offsets = synth.unitigs(args.kmers, k, m, seed=0x5EED0004)
+        lph = build_index(f"cfg4_n{args.kmers}_k{k}_m{m}_u{bits}", bases, offsets, k, m, bits)
+        print(json.dumps(row_query("k63", "BASELINE config 4: synthetic unitigs (62-base overlaps), all members, "
+                                   "128-bit kmer_t, streaming query-p", lph, bits, k, m, bases, offsets,
+                                   True, 32, args.steps)), flush=True)
+
+    if "reads" in args.rows:
+        k, m, bits = B.K, B.M, B.BITS
+        ubases, uoffsets, lph = B.make_workload(args.kmers)
+        # the genome the unitigs were cut from = the unitigs with their (k-1)-base overlaps removed; any long
+        # stretch of it serves as a source of member substrings
+        genome = ubases[: int(uoffsets[-1])]
+        rb, ro = synth.reads(args.reads, genome)
+        print(json.dumps(row_query("reads", f"BASELINE config 5 shape on one GPU: {args.reads} reads of 150 bases, "
+                                   "half substrings of the indexed unitigs with 1% substitutions, half random "
+                                   "(mixed member / non-member k-mers), config-2 index", lph, bits, k, m, rb, ro,
+                                   False, 20000, args.steps)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
