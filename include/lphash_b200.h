@@ -104,6 +104,10 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
                          void* records, uint64_t records_capacity, uint64_t* n_records,
                          uint64_t* n_kmers);
 
+/* The two build-side entry points keep their device workspace per device between calls (a caller
+ * streaming batches does not pay allocation on every batch); this frees it.                      */
+int lphb_scan_release(int device);
+
 /* ---- build-p Part 4: k-mers of colliding minimizers -----------------------------------------
  * Replaces the loop over minimizer::get_colliding_kmers (include/minimizer.hpp:172-319; caller
  * src/partitioned_mphf.cpp:120-129).  ids = ascending minimizer-occurrence ids (classify's second

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_load_file",
            "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
-           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats"]
+           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release"]
 
 _lib = None
 

@@ -8,6 +8,9 @@
 #include <cstring>
 #include <fstream>
 #include <new>
+#include <chrono>
+#include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -586,15 +589,39 @@ namespace {
 
 // Per-call device buffers of the scan pipeline (freed on scope exit).
 struct ScanSession {
-    DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, head_at, tmp, status;
+    DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, head_at, tmp, status, tile_ws;
     cudaStream_t s = nullptr;
     ScanBatch b{};
     uint64_t n_records = 0, n_kmers = 0, tmp_bytes = 0;
     ~ScanSession() {
         for (DevBuf* d : {&bases, &offsets, &code_off, &id_base, &dirty, &head, &pos, &rank, &records,
-                          &head_at, &tmp, &status})
+                          &head_at, &tmp, &status, &tile_ws})
             d->release();
         if (s) cudaStreamDestroy(s);
+    }
+};
+
+// The scan entry points have no handle: their device workspace (a few bytes per base) is kept per
+// device between calls, so that a caller streaming batches does not pay cudaMalloc / cudaFree
+// (both synchronizing) on every batch.  One scan at a time per process; lphb_scan_release frees it.
+std::mutex g_scan_mu;
+ScanSession* g_scan[64] = {};
+ScanSession& scan_session(int device) {
+    if (device < 0 || device >= 64) throw std::invalid_argument("device index out of range");
+    if (!g_scan[device]) g_scan[device] = new ScanSession();
+    return *g_scan[device];
+}
+
+// LPHB_SCAN_TRACE=1: per-stage wall times of the scan on stderr (each mark synchronizes the stream)
+struct ScanTrace {
+    bool on = getenv("LPHB_SCAN_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(cudaStream_t s, const char* what) {
+        if (!on) return;
+        if (s) cudaStreamSynchronize(s);
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lphb scan] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
     }
 };
 
@@ -614,7 +641,7 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     S.n_kmers = n_kmers;
     S.n_records = 0;
     if (n_kmers >= (1ull << 32)) return fail(LPHB_E_ARG, "batch holds >= 2^32 k-mers: split it");
-    CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
+    if (!S.s) CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
     if (n_contigs == 0 || n_kmers == 0) return LPHB_OK;
     if (!bases) return fail(LPHB_E_ARG, "bases is null");
     cudaStream_t s = S.s;
@@ -634,8 +661,11 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     S.tmp_bytes = t1 > t2 ? t1 : t2;
     if (t3 > S.tmp_bytes) S.tmp_bytes = t3;
     S.tmp.reserve(S.tmp_bytes);
+    ScanTrace tr;
+    tr.mark(s, "device allocations");
     CK(cudaMemcpyAsync(S.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(S.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
+    tr.mark(s, "H2D bases + offsets");
     CK(cudaMemsetAsync(S.dirty.p, 0, n_contigs + 8, s));
     CK(cudaMemsetAsync(S.head.p, 0, n_kmers + 8, s));
     auto* st = S.status.as<unsigned long long>();
@@ -656,7 +686,24 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     b.m = m;
     b.seed = seed;
     b.dirty = S.dirty.as<uint8_t>();
-    launch_scan_heads(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), s);
+    {   // pass 1: the tiled kernel where (k, m) is instantiated, else the generic one
+        DevBatch qb{};
+        qb.bases = b.bases;
+        qb.offsets = b.offsets;
+        qb.code_off = b.code_off;
+        qb.n_contigs = n_contigs;
+        qb.first_base = b.first_base;
+        qb.end_base = b.end_base;
+        qb.codes = reinterpret_cast<uint64_t*>(S.pos.p);  // one byte per k-mer (see launch_scan_pos_tiled)
+        qb.dirty = b.dirty;
+        qb.status = st;
+        S.tile_ws.reserve(query_tiled_ws_bytes(span));
+        qb.tile_ws = S.tile_ws.p;
+        qb.tile_ws_bytes = query_tiled_ws_bytes(span);
+        if (launch_scan_pos_tiled(k, m, seed, qb, s)) launch_heads_from_pos(b, S.pos.as<uint8_t>(), S.head.as<uint8_t>(), s);
+        else launch_scan_heads(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), s);
+    }
+    tr.mark(s, "offset scans + pass 1 (heads)");
     launch_count_dirty(b.dirty, n_contigs, st, s);
     launch_head_ranks(S.head.as<uint8_t>(), n_kmers, S.rank.as<uint32_t>(), S.tmp.p, S.tmp_bytes, s);
     unsigned long long h_st[2] = {0, 0};
@@ -669,13 +716,15 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
         return fail(LPHB_E_ARG,
                     "build input contains non-ACGT bytes (the reference's build requires valid "
                     "k-mers only, src/parser_build.cpp:13-16); not supported by the GPU scan yet");
+    tr.mark(s, "head ranks");
     S.n_records = n_rec32;
     S.records.reserve(S.n_records * 18 + 64);
     S.head_at.reserve((S.n_records + 1) * 4);
+    tr.mark(s, "record allocations");
     launch_scan_emit(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), S.rank.as<uint32_t>(),
                      S.records.as<uint8_t>(), S.head_at.as<uint32_t>(), s);
-    launch_scan_sizes(S.head_at.as<uint32_t>(), S.n_records, n_kmers, S.records.as<uint8_t>(), s);
     CK(cudaGetLastError());
+    tr.mark(s, "pass 2 (emit records)");
     return LPHB_OK;
 }
 
@@ -690,7 +739,8 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     if (!offsets || !mm_count || !n_records || !n_kmers) return fail(LPHB_E_ARG, "null argument");
     return guarded([&]() -> int {
         DeviceGuard g(device);
-        ScanSession S;
+        std::lock_guard<std::mutex> lock(g_scan_mu);
+        ScanSession& S = scan_session(device);
         uint64_t mm_out = *mm_count;
         int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
         if (rc != LPHB_OK) return rc;
@@ -707,6 +757,17 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     });
 }
 
+int lphb_scan_release(int device) {
+    return guarded([&]() -> int {
+        std::lock_guard<std::mutex> lock(g_scan_mu);
+        if (device < 0 || device >= 64 || !g_scan[device]) return LPHB_OK;
+        DeviceGuard g(device);
+        delete g_scan[device];
+        g_scan[device] = nullptr;
+        return LPHB_OK;
+    });
+}
+
 int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
                          const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
                          const uint64_t* ids, uint64_t n_ids, int kmer_bits, void* kmers,
@@ -716,7 +777,8 @@ int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     if (k > uint32_t(kmer_bits / 2 - 1)) return fail(LPHB_E_ARG, "k too large for this kmer_t");
     return guarded([&]() -> int {
         DeviceGuard g(device);
-        ScanSession S;
+        std::lock_guard<std::mutex> lock(g_scan_mu);
+        ScanSession& S = scan_session(device);
         uint64_t mm_out = *mm_count;
         int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
         if (rc != LPHB_OK) return rc;

@@ -37,6 +37,12 @@ void launch_query_generic(DevImage const& img, DevBatch const& b, cudaStream_t s
 // of them (the caller then uses the generic kernel).
 bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream);
 
+// Build-side form of the tiled kernel (minimizer::from_string): writes, for every valid k-mer start
+// in dense order (b.code_off layout), the offset of its minimizer inside the k-mer as one byte at
+// reinterpret_cast<uint8_t*>(b.codes); flags contigs with non-ACGT bytes in b.dirty.  Returns false
+// if (k, m) is not instantiated (the caller then uses the generic scan kernel).
+bool launch_scan_pos_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, cudaStream_t stream);
+
 // Exact sequential emulation of the reference's streaming loop for contigs that contain
 // non-ACGT bytes (one thread per listed contig).  out_off[j] = where contig list[j] may write
 // (capacity L - m + 1 each); counts[j] receives how many codes it produced.

@@ -45,6 +45,8 @@
 
 namespace lphb {
 
+uint64_t query_tiled_ws_bytes(uint64_t span_bases);
+
 namespace {
 
 constexpr int kWarps = 4;                      // warps per CTA (independent of each other)
@@ -344,7 +346,11 @@ __device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
     }
 }
 
-template <int K, int M>
+// kScan = true: the build-side form (minimizer::from_string, include/minimizer.hpp:11-170).  Phases A
+// and B only; instead of hash codes the kernel writes, per valid k-mer start and in the same dense
+// order, the offset of its minimizer inside the k-mer (one byte, b.codes reinterpreted), from which
+// the super-k-mer heads follow (scan_kernels.cu).  `f` then only carries k, m and the seed.
+template <int K, int M, bool kScan = false>
 __global__ void __launch_bounds__(kThreads, (Cfg<K, M>::E == 1 ? LPHB_MINB : 4))
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
@@ -634,6 +640,24 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         }
         __syncwarp();
 
+        if constexpr (kScan) {
+            // position-parallel: minimizer offset of every valid k-mer start, dense order
+            uint8_t* outp = reinterpret_cast<uint8_t*>(b.codes) + cur.out;
+            const uint32_t lt = (1u << lane) - 1u;
+            const int lane16 = lane & 16;
+#pragma unroll 4
+            for (int r = 0; r < kTile / 32; ++r) {
+                const int q = lane + r * 32;
+                const uint32_t mw = tile_has_invalid ? s_invalid[r] : 0u;  // uniform in the warp
+                if ((mw >> lane) & 1u) continue;
+                // s_pos holds the position relative to the owning thread's first start (q & ~15)
+                const int p = int(s_pos[q]) + lane16 + r * 32 - q;
+                outp[q - int(s_invpre[r]) - __popc(mw & lt)] = uint8_t(p);
+            }
+            __syncwarp();
+            continue;
+        }
+
         // ------------------------------------------------------------ C: rank the minimizers ----
         // lane l owns mask word l: list index of every marked position
         const uint32_t my_word = s_minmask[lane];
@@ -798,46 +822,47 @@ __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, u
     recs[t] = r;
 }
 
-template <int K, int M>
+template <int K, int M, bool kScan>
 void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaStream_t stream) {
     static bool configured = false;  // per instantiation; the attribute is per device function
     static int resident = 0;         // CTAs that fit the device at once
     if (!configured) {
-        cudaFuncSetAttribute(k_query_tiled<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(k_query_tiled<K, M, kScan>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query_tiled<K, M>, kThreads, kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query_tiled<K, M, kScan>, kThreads, kSmemBytes);
         resident = sms * (per_sm > 0 ? per_sm : 1);
         configured = true;
     }
     // persistent grid: every warp walks tiles (global warp id) + i * (number of warps)
     const uint32_t ctas_needed = (a.n_tiles + kWarps - 1) / kWarps;
     const uint32_t grid = ctas_needed < uint32_t(resident) ? ctas_needed : uint32_t(resident);
-    k_query_tiled<K, M><<<grid, kThreads, kSmemBytes, stream>>>(img, b, a);
+    k_query_tiled<K, M, kScan><<<grid, kThreads, kSmemBytes, stream>>>(img, b, a);
 }
 
-}  // namespace
+using LaunchFn = void (*)(DevImage const&, DevBatch const&, TileArgs const&, cudaStream_t);
 
-uint64_t query_tiled_ws_bytes(uint64_t span_bases) {
-    uint64_t n_tiles = (span_bases + 16) / kMinTile + 2;
-    return n_tiles * sizeof(TileRec) + 64;
-}
-
-bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream) {
-    const uint32_t k = img.k, m = img.m;
-    void (*fn)(DevImage const&, DevBatch const&, TileArgs const&, cudaStream_t) = nullptr;
-    int tile = 0;  // k-mer starts per tile of the instantiation
-#define LPHB_CFG(KK, MM)                  \
-    if (k == KK && m == MM) {             \
-        fn = launch_cfg<KK, MM>;          \
-        tile = Cfg<KK, MM>::Tile;         \
+// the (k, m) pairs the kernel is instantiated for
+bool pick_cfg(uint32_t k, uint32_t m, bool scan, LaunchFn& fn, int& tile) {
+    fn = nullptr;
+#define LPHB_CFG(KK, MM)                                                   \
+    if (k == KK && m == MM) {                                              \
+        fn = scan ? launch_cfg<KK, MM, true> : launch_cfg<KK, MM, false>;  \
+        tile = Cfg<KK, MM>::Tile;                                          \
     }
     LPHB_CFG(31, 20) LPHB_CFG(31, 16) LPHB_CFG(31, 15) LPHB_CFG(31, 17) LPHB_CFG(31, 18) LPHB_CFG(31, 19)
     LPHB_CFG(31, 21) LPHB_CFG(21, 11) LPHB_CFG(15, 7)
     LPHB_CFG(63, 24) LPHB_CFG(47, 20)  // wide windows (W = 40, 28), 128-bit k-mers
 #undef LPHB_CFG
-    if (!fn || !b.tile_ws || b.n_contigs == 0 || b.n_contigs >= (1ull << 32)) return false;
+    return fn != nullptr;
+}
+
+bool launch_tiled(DevImage const& img, DevBatch const& b, bool scan, cudaStream_t stream) {
+    LaunchFn fn;
+    int tile = 0;  // k-mer starts per tile of the instantiation
+    if (!pick_cfg(img.k, img.m, scan, fn, tile)) return false;
+    if (!b.tile_ws || b.n_contigs == 0 || b.n_contigs >= (1ull << 32)) return false;
     if (b.end_base <= b.first_base) return true;
     TileArgs a{};
     const char* p = b.bases + b.first_base;
@@ -851,9 +876,29 @@ bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t str
     if (query_tiled_ws_bytes(b.end_base - b.first_base) > b.tile_ws_bytes) return false;
     TileRec* recs = reinterpret_cast<TileRec*>(b.tile_ws);
     a.recs = recs;
-    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, k, tile, recs);
+    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, img.k, tile, recs);
     fn(img, b, a, stream);
     return true;
+}
+
+}  // namespace
+
+uint64_t query_tiled_ws_bytes(uint64_t span_bases) {
+    uint64_t n_tiles = (span_bases + 16) / kMinTile + 2;
+    return n_tiles * sizeof(TileRec) + 64;
+}
+
+bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream) {
+    return launch_tiled(img, b, false, stream);
+}
+
+bool launch_scan_pos_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, cudaStream_t stream) {
+    DevImage img{};  // the scan form reads k, m and the minimizer seed only
+    img.k = k;
+    img.m = m;
+    img.w = k - m + 1;
+    img.mm_seed = seed;
+    return launch_tiled(img, b, true, stream);
 }
 
 }  // namespace lphb

@@ -108,6 +108,19 @@ __global__ void __launch_bounds__(256) k_scan_heads(const __grid_constant__ Scan
     }
 }
 
+// b(i) = i + pos(i) is the absolute position of k-mer i's minimizer: a record starts where
+// b(i) != b(i-1), i.e. pos(i) + 1 != pos(i-1), and at every contig's first k-mer.
+__global__ void k_heads_from_pos(const uint8_t* pos, uint64_t n, uint8_t* head) {
+    for (uint64_t d = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; d < n; d += uint64_t(gridDim.x) * blockDim.x)
+        head[d] = (d == 0 || uint32_t(pos[d]) + 1u != uint32_t(pos[d - 1])) ? 1 : 0;
+}
+__global__ void k_heads_contig_first(const uint64_t* code_off, uint64_t n_contigs, uint8_t* head) {
+    for (uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; c < n_contigs; c += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t a = code_off[c];
+        if (code_off[c + 1] > a) head[a] = 1;
+    }
+}
+
 struct U8ToU32 {
     __host__ __device__ uint32_t operator()(uint8_t v) const { return v; }
 };
@@ -124,35 +137,61 @@ __device__ __forceinline__ void store_record(uint8_t* rec, uint64_t itself, uint
     rec[16] = p1;
 }
 
+// Pass 2.  A block takes 1024 consecutive k-mers (dense index) at a time; their records are
+// consecutive too (rank is a prefix count).  Step 1 compacts the heads of the chunk into a list
+// (rank - rank of the chunk's first k-mer is the list index), step 2 builds one record per thread
+// with all lanes busy, in shared memory, step 3 writes the chunk's records as one contiguous,
+// coalesced run.  size = distance to the next head (every contig's first k-mer is a head).
+constexpr int kEmitChunk = 1024;
 __global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanBatch b,
                                                    const uint8_t* head, const uint8_t* pos,
                                                    const uint32_t* rank, uint8_t* records,
                                                    uint32_t* head_at) {
-    const uint32_t k = b.k, m = b.m;
-    uint64_t span = b.end_base - b.first_base;
-    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < span;
-         t += uint64_t(gridDim.x) * blockDim.x) {
-        uint64_t i = b.first_base + t;
-        uint64_t c = find_contig(b.offsets, b.n_contigs, i);
-        uint64_t start = __ldg(b.offsets + c), end = __ldg(b.offsets + c + 1);
-        if (i + k > end || b.dirty[c]) continue;
-        uint64_t d = __ldg(b.code_off + c) + (i - start);
-        if (!head[d]) continue;
-        uint32_t r = rank[d];
-        uint64_t bpos = i + pos[d];
-        uint64_t mm = 0;
-        read_mmer(b.bases + bpos, m, mm);
-        store_record(records + 18ull * r, mm, __ldg(b.id_base + c) + (bpos - start), pos[d]);
-        head_at[r] = uint32_t(d);
-    }
-}
-
-__global__ void k_scan_sizes(const uint32_t* head_at, uint64_t n_records, uint64_t n_kmers,
-                             uint8_t* records) {
-    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < n_records;
-         r += uint64_t(gridDim.x) * blockDim.x) {
-        uint64_t next = r + 1 < n_records ? head_at[r + 1] : n_kmers;
-        records[18 * r + 17] = uint8_t(next - head_at[r]);
+    __shared__ __align__(16) uint16_t s_rec[kEmitChunk * 9];
+    __shared__ uint16_t s_list[kEmitChunk];
+    const uint32_t m = b.m;
+    const uint64_t n = b.n_kmers;
+    for (uint64_t d0 = uint64_t(blockIdx.x) * kEmitChunk; d0 < n; d0 += uint64_t(gridDim.x) * kEmitChunk) {
+        const uint64_t d1 = d0 + kEmitChunk < n ? d0 + kEmitChunk : n;
+        const uint32_t r0 = rank[d0], r1 = rank[d1];
+        // contig of the chunk's first k-mer, once per chunk (same addresses in every thread); a record
+        // then walks forward from it (a chunk rarely spans more than a few contigs)
+        const uint64_t c0 = find_contig(b.code_off, b.n_contigs, d0);
+        for (uint64_t d = d0 + threadIdx.x; d < d1; d += blockDim.x)
+            if (head[d]) s_list[rank[d] - r0] = uint16_t(d - d0);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < r1 - r0; t += blockDim.x) {
+            const uint64_t d = d0 + s_list[t];
+            // last contig whose first k-mer is at or before d (contigs without k-mers share their successor's offset)
+            uint64_t c = c0;
+            while (c + 1 < b.n_contigs && __ldg(b.code_off + c + 1) <= d) ++c;
+            const uint64_t start = __ldg(b.offsets + c);
+            const uint64_t i = start + (d - __ldg(b.code_off + c));
+            const uint32_t p1 = pos[d];
+            const char* s = b.bases + i + p1;
+            uint64_t mm = 0;
+#pragma unroll
+            for (int j = 0; j < 31; ++j)
+                if (j < int(m)) mm = (mm << 2) | (nt4(uint8_t(s[j])) & 3u);
+            uint64_t e;  // next head
+            if (t + 1 < r1 - r0) {
+                e = d0 + s_list[t + 1];
+            } else {
+                e = d1;
+                while (e < n && !head[e]) ++e;
+            }
+            const uint64_t id = __ldg(b.id_base + c) + (i + p1 - start);
+            uint16_t* q = s_rec + t * 9;  // 18-byte packed mm_record_t (constants.hpp:26-33)
+            q[0] = uint16_t(mm); q[1] = uint16_t(mm >> 16); q[2] = uint16_t(mm >> 32); q[3] = uint16_t(mm >> 48);
+            q[4] = uint16_t(id); q[5] = uint16_t(id >> 16); q[6] = uint16_t(id >> 32); q[7] = uint16_t(id >> 48);
+            q[8] = uint16_t(p1 | (uint32_t(e - d) << 8));
+            head_at[r0 + t] = uint32_t(d);
+        }
+        __syncthreads();
+        uint16_t* dst = reinterpret_cast<uint16_t*>(records) + uint64_t(r0) * 9;  // records are 2-byte aligned
+        const uint32_t n16 = (r1 - r0) * 9;
+        for (uint32_t t = threadIdx.x; t < n16; t += blockDim.x) dst[t] = s_rec[t];
+        __syncthreads();
     }
 }
 
@@ -237,6 +276,12 @@ void launch_scan_heads(ScanBatch const& b, uint8_t* head, uint8_t* pos, cudaStre
     k_scan_heads<<<grid_for(span), 256, 0, stream>>>(b, head, pos);
 }
 
+void launch_heads_from_pos(ScanBatch const& b, const uint8_t* pos, uint8_t* head, cudaStream_t stream) {
+    if (!b.n_kmers) return;
+    k_heads_from_pos<<<grid_for(b.n_kmers), 256, 0, stream>>>(pos, b.n_kmers, head);
+    k_heads_contig_first<<<grid_for(b.n_contigs), 256, 0, stream>>>(b.code_off, b.n_contigs, head);
+}
+
 uint64_t head_ranks_tmp_bytes(uint64_t n_kmers) {
     size_t bytes = 0;
     cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(nullptr, U8ToU32{});
@@ -261,15 +306,8 @@ void launch_head_ranks(const uint8_t* head, uint64_t n_kmers, uint32_t* rank, vo
 
 void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
                       const uint32_t* rank, uint8_t* records, uint32_t* head_at, cudaStream_t stream) {
-    uint64_t span = b.end_base - b.first_base;
-    if (!span) return;
-    k_scan_emit<<<grid_for(span), 256, 0, stream>>>(b, head, pos, rank, records, head_at);
-}
-
-void launch_scan_sizes(const uint32_t* head_at, uint64_t n_records, uint64_t n_kmers,
-                       uint8_t* records, cudaStream_t stream) {
-    if (!n_records) return;
-    k_scan_sizes<<<grid_for(n_records), 256, 0, stream>>>(head_at, n_records, n_kmers, records);
+    if (!b.n_kmers) return;
+    k_scan_emit<<<grid_for((b.n_kmers + 3) / 4), 256, 0, stream>>>(b, head, pos, rank, records, head_at);
 }
 
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,

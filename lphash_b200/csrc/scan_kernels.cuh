@@ -25,6 +25,9 @@ void launch_id_base(const uint64_t* d_offsets, uint64_t n_contigs, uint32_t m, u
 // Pass 1: head[d] = 1 where k-mer d starts a super-k-mer, pos[d] = offset of its minimizer.
 void launch_scan_heads(ScanBatch const& b, uint8_t* head, uint8_t* pos, cudaStream_t stream);
 
+// Pass 1 when pos[] came from the tiled kernel (launch_scan_pos_tiled): head flags from pos alone.
+void launch_heads_from_pos(ScanBatch const& b, const uint8_t* pos, uint8_t* head, cudaStream_t stream);
+
 // rank[d] = number of heads before d (exclusive); rank[n_kmers] = number of records.
 void launch_head_ranks(const uint8_t* head, uint64_t n_kmers, uint32_t* rank, void* d_tmp,
                        uint64_t tmp_bytes, cudaStream_t stream);
@@ -33,8 +36,6 @@ uint64_t head_ranks_tmp_bytes(uint64_t n_kmers);
 // Pass 2: write the 18-byte records {itself, id, p1, size} and head_at[r] = dense index of record r.
 void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
                       const uint32_t* rank, uint8_t* records, uint32_t* head_at, cudaStream_t stream);
-void launch_scan_sizes(const uint32_t* head_at, uint64_t n_records, uint64_t n_kmers,
-                       uint8_t* records, cudaStream_t stream);
 
 // get_colliding_kmers: take[r] = (record r's id is in ids) ? size : 0 ...
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
