@@ -193,3 +193,46 @@ def test_scan_then_classify_feeds_the_same_keys(golden):
     trip, ids = oracle.classify(rec)
     assert np.array_equal(trip, golden.triplets)
     assert np.array_equal(ids, golden.coll_ids)
+
+
+def test_scan_workspace_is_reused_and_released():
+    """The scan keeps its device workspace between calls (lphb_scan_release frees it): calls of
+    growing, shrinking and different-(k, m) batches must not see each other's leftovers."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    for k, m, n in [(31, 20, 4000), (31, 20, 90000), (63, 24, 7000), (31, 20, 500), (25, 13, 20000)]:
+        lens = rng.integers(k, 4 * k + 200, size=max(1, n // (2 * k + 100)))
+        bases = synth.random_bases(int(lens.sum()), rng)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        want, wk, wmm = oracle.scan(bases, offsets, k, m, mode=0)
+        got, gk, gmm = api.scan_superkmers(bases, offsets, k, m)
+        assert (gk, gmm) == (wk, wmm)
+        assert np.array_equal(got, want), (k, m, n)
+    assert api.lib().lphb_scan_release(0) == 0
+    assert api.lib().lphb_scan_release(0) == 0  # idempotent
+    got, gk, gmm = api.scan_superkmers(bases, offsets, k, m)  # allocates again
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["k63_m24_u128", "k47_m20_u128", "k40_m17_u128"])
+def test_wide_windows_long_contigs_match_oracle(name, handles):
+    """Windows wider than one thread segment (W = 40, 28 on the tiled kernel; W = 24 generic): long
+    contigs, so that most tiles lie inside one contig, plus seams every few tiles."""
+    g = load_golden(name)
+    f = handles(name)
+    o = oracle.OracleMphf(g.lph, g.bits)
+    rng = np.random.Generator(np.random.PCG64(0xD1CE + g.k))
+    genome = g.index_bases[: int(g.index_offsets[len(g.index_offsets) // 2])]
+    lens = [5000, 2999, g.k, 12345, g.k + 1, 931, 929, 1857]
+    recs = []
+    for ln in lens:
+        lo = int(rng.integers(0, max(1, len(genome) - ln)))
+        s = genome[lo:lo + ln].copy()
+        if len(s) < ln:
+            s = np.concatenate([s, synth.random_bases(ln - len(s), rng)])
+        recs.append(s)
+    bases = np.concatenate(recs)
+    offsets = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+    want, want_off = o.query_batch(bases, offsets)
+    got, got_off = f.query_batch(bases, offsets)
+    assert np.array_equal(got_off, want_off)
+    assert np.array_equal(got, want)

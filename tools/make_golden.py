@@ -2,7 +2,7 @@
 """Generates the golden fixtures under tests/golden/ FROM THE UNMODIFIED REFERENCE
 (oracle/_ref/libref{64,128}.so, built by oracle/build_ref.sh from /root/reference).
 
-Run here (where /root/reference exists):   python tools/make_golden.py
+Run here (where /root/reference exists):   python tools/make_golden.py [NAME ...]   (default: all)
 The fixtures are committed so that the oracle and the CUDA path can be checked against the
 reference's own outputs on the GPU box, where the reference tree does not exist.
 
@@ -39,7 +39,10 @@ FIXTURES = [("k31_m20_u64", 31, 20, 64, 24000, 0xA001),
             ("k63_m24_u128", 63, 24, 128, 24000, 0xA003),
             ("k47_m20_u128", 47, 20, 128, 16000, 0xA004),
             ("k15_m7_u64", 15, 7, 64, 12000, 0xA005),
-            ("k21_m11_u64", 21, 11, 64, 12000, 0xA006)]
+            ("k21_m11_u64", 21, 11, 64, 12000, 0xA006),
+            # (k, m) pairs the tiled kernel is NOT instantiated for: the generic query / scan kernels
+            ("k25_m13_u64", 25, 13, 64, 12000, 0xA007),
+            ("k40_m17_u128", 40, 17, 128, 12000, 0xA008)]
 
 
 def make_queries(bases, offsets, k, m, seed):
@@ -102,7 +105,10 @@ def make_queries(bases, offsets, k, m, seed):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, k, m, bits, n_kmers, seed in FIXTURES:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             bases, offsets = synth.unitigs(n_kmers, k, m, seed=seed, min_len=2 * k, max_len=3000,
                                            planted=8)
