@@ -62,12 +62,23 @@ def make_workload(n_kmers: int):
         fa = os.path.join(CACHE, tag + ".fa")
         synth.write_fasta(fa, bases, offsets)
         t0 = time.time()
-        threads = os.cpu_count() or 1
-        csv = ref.build(fa, K, M, lph + ".tmp", bits=BITS, threads=min(threads, 32), tmp_dir=CACHE)
+        csv = ref.build(fa, K, M, lph + ".tmp", bits=BITS, threads=min(host_threads(), 32), tmp_dir=CACHE)
         os.replace(lph + ".tmp", lph)
         os.remove(fa)
         log(f"[bench] reference build-p: {csv} ({time.time() - t0:.1f}s)")
     return bases, offsets, lph
+
+
+def host_threads() -> int:
+    """Cores this process may run on (a container's cpuset can be far smaller than os.cpu_count())."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def index_path(n_kmers: int) -> str:
+    return os.path.join(CACHE, f"cfg2_n{n_kmers}_k{K}_m{M}_u{BITS}.lph")
 
 
 def rotate_contigs(bases, offsets, r: int):
@@ -165,7 +176,7 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     bases, offsets, lph = make_workload(args.kmers)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     # bounded sample: the full config-2 set is ~4 thread-seconds of CPU work per pass
     n, times = cpu_reference_run(bases, offsets, lph, args.steps, min(args.warmup, 1), threads)
     t = float(np.sum(times))
@@ -204,17 +215,23 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Input preparation comes before any collective: if the index is not in bench_cache/ yet (build()
+    # in __graft_entry__ prepares it where the reference tree exists), rank 0 builds it with the
+    # reference's build-p while the other ranks wait on the FILE, not inside an NCCL barrier (whose
+    # watchdog would fire during a long build).
+    if rank != 0:
+        t_wait = time.time()
+        while not os.path.exists(index_path(args.kmers)):
+            if time.time() - t_wait > 7200:
+                raise RuntimeError("rank 0 did not produce the index within 2 h")
+            time.sleep(1.0)
+    bases, offsets, lph = make_workload(args.kmers)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"),
+                                timeout=datetime.timedelta(minutes=30))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-
-    if rank == 0:
-        bases, offsets, lph = make_workload(args.kmers)
-    if world > 1:
-        dist.barrier()
-        if rank != 0:
-            bases, offsets, lph = make_workload(args.kmers)  # cache hit: index already built
     bases, offsets = rotate_contigs(bases, offsets, rank)
     f = api.Mphf.load(lph, BITS, device=local)
     n_contigs = len(offsets) - 1
@@ -339,7 +356,7 @@ def run_ours(args):
                              "input_only_frac": (algo_bytes - 8 * n_kmers) / (kern_ms * 1e-3) / 1e9 / peak},
                 "cpu_baseline": None}
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             try:
                 n, times = cpu_reference_run(bases, offsets, lph, steps=3, warmup=1, threads=threads)
                 line["cpu_baseline"] = {"value": n * len(times) / float(np.sum(times)), "unit": "k-mers/s",

@@ -44,7 +44,7 @@ def build_index(tag, bases, offsets, k, m, bits):
         fa = os.path.join(B.CACHE, tag + ".fa")
         synth.write_fasta(fa, bases, offsets)
         t0 = time.time()
-        csv = ref.build(fa, k, m, lph + ".tmp", bits=bits, threads=min(os.cpu_count() or 1, 32), tmp_dir=B.CACHE)
+        csv = ref.build(fa, k, m, lph + ".tmp", bits=bits, threads=min(B.host_threads(), 32), tmp_dir=B.CACHE)
         os.replace(lph + ".tmp", lph)
         os.remove(fa)
         B.log(f"[rows] reference build-p {tag}: {csv} ({time.time() - t0:.1f}s)")
@@ -115,7 +115,7 @@ def row_query(name, workload, lph, bits, k, m, bases, offsets, members_all, orac
     cpu = None
     try:
         from oracle import ref
-        threads = os.cpu_count() or 1
+        threads = B.host_threads()
         r = ref.RefMphf(lph, bits)
         sb, so = prefix_batch(bases, offsets, max(64, (len(offsets) - 1) // 4))
         secs, n, _, _ = r.query_batch(sb, so, threads=threads, want_codes=False)
