@@ -171,6 +171,13 @@ template <class Accumulator>
     return n_kmers;
 }
 
+// Frees the device workspace the two build-side calls keep between calls (call after the loop over
+// from_string / get_colliding_kmers, i.e. after src/partitioned_mphf.cpp:77 and :129).
+inline void release_workspace(int device = 0) {
+    int rc = lphb_scan_release(device);
+    if (rc != LPHB_OK) detail::raise("lphash_b200::minimizer::release_workspace", rc);
+}
+
 // Batch form: the whole input (or a large slab of it) in one call; records land in `records` in
 // scan order.  Returns the number of k-mers.
 inline uint64_t from_batch(const char* bases, const uint64_t* offsets, uint64_t n_contigs, uint32_t k,
