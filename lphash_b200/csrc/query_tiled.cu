@@ -59,13 +59,18 @@ constexpr int kStrips = 2;                     // passes per tile
 constexpr int kMinTile = kStrips * 29 * kS;    // smallest tile (bounds the set-up workspace)
 constexpr int kSlots = 1024;                   // positions a minimizer of the tile's k-mers can sit at (tile + < 64)
 constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
+// tuned on B200 (profiles/r01c_experiments.md): 2 probes per lane in flight, 5 CTAs per SM (102 registers, no spills)
 #ifndef LPHB_PROBES
-#define LPHB_PROBES 3
+#define LPHB_PROBES 2
 #endif
 #ifndef LPHB_MINB
-#define LPHB_MINB 6
+#define LPHB_MINB 5
+#endif
+#ifndef LPHB_EMIT_UNROLL
+#define LPHB_EMIT_UNROLL 8
 #endif
 constexpr int kProbes = LPHB_PROBES;           // probes a lane keeps in flight
+constexpr int kEmitUnroll = LPHB_EMIT_UNROLL;  // rows of the plain emit in flight
 constexpr int kGroups = 6;                     // 32-probe groups whose results a warp holds at once
 constexpr int kCap = 32 * kGroups;             // = 192 (the list index fits a byte)
 struct Entry {                                 // code of the k-mer at tile-local q = B + ns * q (mod 2^64)
@@ -296,7 +301,7 @@ __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const
     const uint8_t* pos_l = s_pos + lane;
     const uint8_t* ref_l = s_ref + (lane & 16);
     uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
-#pragma unroll 8
+#pragma unroll kEmitUnroll
     for (int r = 0; r < kTile / 32; ++r) {
         const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) tile-local position of the minimizer
         const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
