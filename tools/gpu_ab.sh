@@ -1,13 +1,13 @@
 #!/usr/bin/env bash
-# One gpurun call: GPU parity tests, then the bench line for the given LPHB_QUERY_IMPL values.
-# Usage: tools/gpu_ab.sh <tag> [impl...]   (impl: pipe tiled)
+# One gpurun call: GPU parity tests, then one short bench line per label (labels only name the output files).
+# Usage: tools/gpu_ab.sh <tag> [label...]
 set -u
 TAG="$1"; shift
 OUT="gpurun_out/$TAG"; mkdir -p "$OUT"
 timeout 900 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
 echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log"
 for v in "$@"; do
-  LPHB_QUERY_IMPL=$v timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$OUT/bench_$v.json" 2> "$OUT/bench_$v.err"
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$OUT/bench_$v.json" 2> "$OUT/bench_$v.err"
   python - "$v" "$OUT/bench_$v.json" <<'PY'
 import json,sys
 try:

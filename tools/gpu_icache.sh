@@ -7,7 +7,7 @@ M=gpu__time_duration.sum,sm__icc_request_hit_rate.pct,sm__icc_requests.sum,gcc__
 for v in "$@"; do
   lib="$PWD/lphash_b200/liblphash_b200_$v.so"; [ "$v" = default ] && lib="$PWD/lphash_b200/liblphash_b200.so"
   for impl in tiled; do
-    LPHB_BENCH_NOCHECK=1 LPHB_QUERY_IMPL=$impl LPHASH_B200_LIB="$lib" timeout 600 ncu --metrics $M --clock-control none --cache-control none -k regex:k_query_ -s 5 -c 1 --csv --log-file "$OUT/ic_${v}_$impl.csv" python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/ic_${v}_$impl.log" 2>&1
+    LPHB_BENCH_NOCHECK=1 LPHASH_B200_LIB="$lib" timeout 600 ncu --metrics $M --clock-control none --cache-control none -k regex:k_query_ -s 5 -c 1 --csv --log-file "$OUT/ic_${v}_$impl.csv" python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/ic_${v}_$impl.log" 2>&1
     echo "== $v $impl"; python - "$OUT/ic_${v}_$impl.csv" <<'PY'
 import csv,sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>10]
