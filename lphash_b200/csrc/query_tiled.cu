@@ -311,12 +311,34 @@ __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const
     }
 }
 
+// Masked form: like the plain form, for a tile that does contain starts without a code (contig
+// seams: every tile of a batch of short reads): the (warp-uniform) word of the invalid-start mask
+// predicates the store and compacts the output index.
+template <int kTile>
+__device__ __forceinline__ void emit_masked(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
+                                            const Entry* s_ent, uint32_t hi, const uint32_t* s_invalid,
+                                            const uint16_t* s_invpre, uint64_t* out_tile) {
+    const uint8_t* pos_l = s_pos + lane;
+    const uint8_t* ref_l = s_ref + (lane & 16);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
+#pragma unroll 2
+    for (int r = 0; r < kTile / 32; ++r) {
+        const uint32_t mw = s_invalid[r];  // uniform in the warp
+        const int mp = int(pos_l[r * 32]) + r * 32;
+        const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
+        uint32_t lo;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
+        if (!((mw >> lane) & 1u)) __stcs(o + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), make_uint2(lo, hi));
+    }
+}
+
 // General form.  Per group of 32 starts the (warp-uniform) word of the invalid-start mask tells
 // whether starts without a code (contig seams) must be skipped and the output index compacted;
 // k-mers of colliding minimizers are flagged in s_fbmask; kChunked (more than kCap minimizers):
 // entries outside [i0, i1) are left to their own chunk.
 template <int kTile, bool kChunked>
-__device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
+static __device__ __noinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
                                              const uint8_t* s_pos, const uint8_t* s_ref,
                                              const uint32_t* s_minmask, const uint16_t* s_wpre,
                                              const Entry* s_ent, const uint32_t* s_hi,
@@ -349,6 +371,96 @@ __device__ __forceinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
         const uint64_t code = B + uint64_t(int64_t(e.ns) * int64_t(q));
         __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), code);
     }
+}
+
+// k-mer starts of a tile that produce no code (contig seams, short contigs, positions outside
+// [first, end)) -> s_invalid.  Only for tiles that one contig does not cover: out of line, away from
+// the hot loop's instruction-cache footprint.
+template <int K, int kTile>
+static __device__ __noinline__ void mark_invalid(DevBatch const& b, uint32_t* s_invalid, int lane, int64_t T0,
+                                                 uint32_t c0) {
+    constexpr int kMaskWords = kTile / 32;
+    const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
+    const int64_t tile_end = T0 + kTile;
+    if (T0 < first) {  // head padding of the first tile (< 16 positions)
+        int n = int(first - T0);
+        if (lane == 0) atomicOr(&s_invalid[0], (1u << n) - 1u);
+    }
+    uint64_t c = c0;
+    for (;; c += 32) {
+        uint64_t cc = c + lane;
+        bool live = cc < b.n_contigs;
+        int64_t s = live ? int64_t(__ldg(b.offsets + cc)) : end;
+        int64_t e = live ? int64_t(__ldg(b.offsets + cc + 1)) : end;
+        if (live && s < tile_end) {
+            // starts in [max(e-K+1, s), e) have fewer than K bases left in their contig
+            int64_t lo = e - (K - 1) > s ? e - (K - 1) : s;
+            int64_t hi = e;
+            if (lo < T0) lo = T0;
+            if (hi > tile_end) hi = tile_end;
+            for (int64_t q = lo; q < hi;) {
+                int ql = int(q - T0);
+                int wbit = ql & 31;
+                int n = int(hi - q) < 32 - wbit ? int(hi - q) : 32 - wbit;
+                uint32_t bits = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << wbit;
+                atomicOr(&s_invalid[ql >> 5], bits);
+                q += n;
+            }
+        }
+        // go on while the contig after lane 31's also starts inside the tile
+        if (!__any_sync(0xFFFFFFFFu, lane == 31 && live && e < tile_end)) break;
+    }
+    if (end < tile_end) {  // past the last base of the batch
+        int lo = end > T0 ? int(end - T0) : 0;
+        if (lane >= (lo >> 5) && lane < kMaskWords) {
+            uint32_t bits = 0xFFFFFFFFu;
+            if (lane == (lo >> 5)) bits <<= (lo & 31);
+            atomicOr(&s_invalid[lane], bits);
+        }
+    }
+    __syncwarp();
+}
+
+// Colliding minimizers: every k-mer of the run goes through fallback_kmer_order
+// (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134).  Lane l takes bit l of every mask
+// word, so the consecutive k-mers of a run spread over the lanes and their (dependent, uncached)
+// gathers overlap.  Rare: out of line.
+template <int K, int M, int kTile>
+static __device__ __noinline__ void fallback_kmers(DevImage const& f, const uint32_t* s_packed, uint32_t* s_fbmask,
+                                                   const uint32_t* s_invalid, const uint16_t* s_invpre, int lane,
+                                                   uint64_t* out) {
+    constexpr int NW = Cfg<K, M>::NW, kMaskWords = kTile / 32;
+#pragma unroll 1
+    for (int r = 0; r < kMaskWords; ++r) {
+        const uint32_t fw = s_fbmask[r];  // uniform
+        if (!((fw >> lane) & 1u)) continue;
+        const int g = r * 32 + lane;
+        const int wi = g >> 4, sh2 = (g & 15) * 2;
+        uint32_t x[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
+        uint32_t y[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], sh2);
+        // y[0..3] = 128-bit window starting at base g (y[0] most significant)
+        uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
+        uint64_t klo, khi;
+        if constexpr (K <= 32) {
+            klo = top >> (64 - 2 * K);
+            khi = 0;
+            (void)bot;
+        } else {
+            constexpr int sh = 128 - 2 * K;  // 2..62
+            klo = (bot >> sh) | (top << (64 - sh));
+            khi = top >> sh;
+        }
+        const uint32_t mw = s_invalid[r];
+        const int oidx = g - int(s_invpre[r] + __popc(mw & ((1u << lane) - 1u)));
+        out[oidx] = fallback_code(f, klo, khi);
+    }
+    __syncwarp();
+    if (lane < kMaskWords) s_fbmask[lane] = 0;
+    __syncwarp();
 }
 
 // kScan = true: the build-side form (minimizer::from_string, include/minimizer.hpp:11-170).  Phases A
@@ -444,7 +556,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         s_invalid[lane] = 0;
         mbar_wait(&s_mbar[buf], (iter >> 1) & 1u);
         const int n_words = int(tile_bytes(tile) >> 4);
-#pragma unroll
+#pragma unroll 1
         for (int t = lane; t < kPackedSlots; t += 32) {
             uint32_t word = 0;
             if (t < n_words) {
@@ -461,46 +573,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         // k-mer starts that produce no code (contig seams, short contigs, positions outside
         // [first, end)) -> s_invalid; nothing to do when one contig covers the tile and k-1 more bases
         const bool tile_clean = cur.clean != 0;
-        if (!tile_clean) {
-            const int64_t tile_end = T0 + kTile;
-            if (T0 < first) {  // head padding of the first tile (< 16 positions)
-                int n = int(first - T0);
-                if (lane == 0) atomicOr(&s_invalid[0], (1u << n) - 1u);
-            }
-            uint64_t c = cur.c0;
-            for (;; c += 32) {
-                uint64_t cc = c + lane;
-                bool live = cc < b.n_contigs;
-                int64_t s = live ? int64_t(__ldg(b.offsets + cc)) : end;
-                int64_t e = live ? int64_t(__ldg(b.offsets + cc + 1)) : end;
-                if (live && s < tile_end) {
-                    // starts in [max(e-K+1, s), e) have fewer than K bases left in their contig
-                    int64_t lo = e - (K - 1) > s ? e - (K - 1) : s;
-                    int64_t hi = e;
-                    if (lo < T0) lo = T0;
-                    if (hi > tile_end) hi = tile_end;
-                    for (int64_t q = lo; q < hi;) {
-                        int ql = int(q - T0);
-                        int wbit = ql & 31;
-                        int n = int(hi - q) < 32 - wbit ? int(hi - q) : 32 - wbit;
-                        uint32_t bits = (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)) << wbit;
-                        atomicOr(&s_invalid[ql >> 5], bits);
-                        q += n;
-                    }
-                }
-                // go on while the contig after lane 31's also starts inside the tile
-                if (!__any_sync(0xFFFFFFFFu, lane == 31 && live && e < tile_end)) break;
-            }
-            if (end < tile_end) {  // past the last base of the batch
-                int lo = end > T0 ? int(end - T0) : 0;
-                if (lane >= (lo >> 5) && lane < kMaskWords) {
-                    uint32_t bits = 0xFFFFFFFFu;
-                    if (lane == (lo >> 5)) bits <<= (lo & 31);
-                    atomicOr(&s_invalid[lane], bits);
-                }
-            }
-            __syncwarp();
-        }
+        if (!tile_clean) mark_invalid<K, kTile>(b, s_invalid, lane, T0, cur.c0);
         // exclusive prefix of invalid counts per mask word (one word per lane)
         bool tile_has_invalid = false;
         {
@@ -761,44 +834,21 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             // colliding minimizer, no start without a code, one chunk
             const uint32_t hi_warp = __shfl_sync(0xFFFFFFFFu, hi0, 0);
             special |= have && hi0 != hi_warp;
-            const bool plain = !chunked && !tile_has_invalid && !__any_sync(0xFFFFFFFFu, special);
+            const bool simple = !chunked && !__any_sync(0xFFFFFFFFu, special);
+            const bool plain = simple && !tile_has_invalid;
             __syncwarp();
             if (plain) emit_plain<kTile>(lane, s_pos, s_ref, s_ent, hi_warp, out);
+            else if (simple) emit_masked<kTile>(lane, s_pos, s_ref, s_ent, hi_warp, s_invalid, s_invpre, out);
             else if (!chunked) emit_general<kTile, false>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
             else emit_general<kTile, true>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
             __syncwarp();
 
-            // colliding minimizers: every k-mer of the run goes through fallback_kmer_order
-            // (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134)
-            uint32_t fbw = lane < kMaskWords ? s_fbmask[lane] : 0u;  // lane l owns k-mers 32 l .. 32 l + 31
-            if (fbw) s_fbmask[lane] = 0;
-            while (fbw) {
-                const int g = lane * 32 + (__ffs(fbw) - 1);
-                fbw &= fbw - 1;
-                const int wi = g >> 4, r = (g & 15) * 2;
-                uint32_t x[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
-                uint32_t y[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], r);
-                // y[0..3] = 128-bit window starting at base g (y[0] most significant)
-                uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
-                uint64_t klo, khi;
-                if constexpr (K <= 32) {
-                    klo = top >> (64 - 2 * K);
-                    khi = 0;
-                    (void)bot;
-                } else {
-                    constexpr int sh = 128 - 2 * K;  // 2..62
-                    klo = (bot >> sh) | (top << (64 - sh));
-                    khi = top >> sh;
-                }
-                const uint32_t mw = s_invalid[g >> 5];
-                const int oidx = g - int(s_invpre[g >> 5] + __popc(mw & ((1u << (g & 31)) - 1u)));
-                out[oidx] = fallback_code(f, klo, khi);
+            // colliding minimizers: every k-mer of the run goes through fallback_kmer_order (rare)
+            if (!simple) {
+                const uint32_t fb_any = lane < kMaskWords ? s_fbmask[lane] : 0u;
+                if (__any_sync(0xFFFFFFFFu, fb_any != 0))
+                    fallback_kmers<K, M, kTile>(f, s_packed, s_fbmask, s_invalid, s_invpre, lane, out);
             }
-            __syncwarp();
         }
     }  // tiles of this warp
 }
