@@ -1,42 +1,53 @@
-// Streaming-query kernel (the hot path) for window widths W = k-m+1 <= 17.
+// Streaming-query kernel (the hot path) and its build-side (scan) form, for the (k, m) pairs listed
+// in pick_cfg(): window widths W = k-m+1 up to 49.
 //
-// The concatenated base stream is cut into WARP TILES of 992 k-mer starts (2 strips x 31 lanes x
-// 16 starts).  The grid is persistent (as many CTAs as fit the GPU); every WARP walks its own
-// sequence of tiles (tile = global warp id, + number of warps, ...) and owns all the shared memory
-// it touches, so there is no CTA barrier anywhere: a warp stalled on a probe never holds up the
-// others.  Per tile:
+// The concatenated base stream is cut into WARP TILES of 2 strips x (32-E) lanes x 16 k-mer starts,
+// E = number of lanes to the right a thread's windows reach into (1 for W <= 17: 992 starts per tile;
+// 2 for W <= 33: 960; 3 for W <= 49: 928).  The grid is persistent (as many CTAs as fit the GPU);
+// every WARP walks its own sequence of tiles (tile = global warp id, + number of warps, ...) and owns
+// all the shared memory it touches, so there is no CTA barrier anywhere: a warp stalled on a probe
+// never holds up the others.  Per tile:
 //
-//  A  stage+pack   the tile's ASCII bytes (1040 B incl. k-1 bases of overlap) arrive in shared
-//                  memory by ONE TMA bulk copy (cp.async.bulk -> mbarrier), issued one tile ahead
-//                  (double buffer), so the global-load latency is never exposed.  Each lane then
-//                  packs 16-byte words to 32-bit words of 2-bit codes (first base in the most
-//                  significant bits, the reference's m-mer / k-mer orientation,
-//                  partitioned_mphf.hpp:106-108).  Non-ACGT bytes flag their contig dirty (it is
-//                  then recomputed by the exact sequential kernel).  Contig seams
-//                  are rasterised into a bitmask of k-mer starts that produce no code (skipped
-//                  entirely when the tile lies inside one contig, which the set-up kernel records).
+//  A  stage+pack   the tile's ASCII bytes (incl. k-1 bases of overlap) arrive in shared memory by ONE
+//                  TMA bulk copy (cp.async.bulk -> mbarrier), issued one tile ahead (double buffer),
+//                  so the global-load latency is never exposed.  Each lane then packs 16-byte words
+//                  to 32-bit words of 2-bit codes (first base in the most significant bits, the
+//                  reference's m-mer / k-mer orientation, partitioned_mphf.hpp:106-108).  Non-ACGT
+//                  bytes flag their contig dirty (it is then recomputed by the exact sequential
+//                  kernel).  Contig seams are rasterised into a bitmask of k-mer starts
+//                  that produce no code (skipped entirely when the tile lies inside one contig, which
+//                  the set-up kernel records).
 //  B  scan         each thread owns 16 consecutive k-mer starts.  16 m-mer hashes from registers
-//                  (MurmurHash2-64, seeded); each is reduced to a 32-bit key = top 27 bits of the
-//                  hash | 5-bit thread-local position, so that ONE unsigned min picks the smaller
-//                  hash and, between equal keys, the leftmost.  The W-1 keys a thread lacks come
-//                  from lane+1 by warp shuffle (lane 31 only feeds lane 30).  Sliding minimum =
-//                  sparse table of 3-input minima (VIMNMX3): spans of 3, 9, then two spans cover
-//                  the window.  A second pass with the position bits complemented finds the
-//                  RIGHTMOST minimum; if the two differ anywhere the 27-bit keys tied (true repeat
-//                  or truncation tie) and that thread recomputes its 16 windows from the full
-//                  64-bit hashes (out of line, rare).  Result: minimizer offset of every k-mer +
-//                  mask of positions that are some k-mer's minimizer.
+//                  (MurmurHash2-64, seeded); each is reduced to a 32-bit key = top bits of the hash |
+//                  thread-local position (5 bits, 6 for wide windows), so that ONE unsigned min picks
+//                  the smaller hash and, between equal key prefixes, the leftmost.
+//                  W <= 17: the W-1 keys a thread lacks come from lane+1 by warp shuffle; sliding
+//                  minimum = sparse table of 3-input minima (VIMNMX3).  Wider windows: prefix / suffix
+//                  minima of the thread's own keys + one neighbour prefix value (and whole-block
+//                  minima) per window by shuffle, position field rebased by 16 per lane.
+//                  A second pass with the position bits complemented finds the RIGHTMOST minimum; if
+//                  the two differ anywhere two candidates shared a key prefix (true repeat or
+//                  truncation tie) and that thread recomputes its 16 windows from the full 64-bit
+//                  hashes (out of line, rare).  Result: minimizer offset of every k-mer + mask of
+//                  positions that are some k-mer's minimizer.
+//                  [scan form: the offsets are written out, one byte per valid start, and the tile ends]
 //  C  compact      minimizer positions of the tile -> dense list in shared memory (warp scan).
 //  D  probe        one lane per distinct minimizer position, kProbes in flight per lane:
 //                  m-mer -> PTHash (one 8-byte gather) -> bucket table (one 4/8-byte gather)
 //                  (device_mphf.cuh) -> {B, ns} with  code(k-mer at q) = B + ns * q.
 //  E  emit         position-parallel: lane l handles k-mers l, l+32, ...: two byte loads find the
-//                  entry, one multiply-add makes the code, 8-byte stores are fully coalesced.
-//                  K-mers of colliding minimizers are flagged and resolved through
-//                  fallback_kmer_order (partitioned_mphf.cpp:308-313).
+//                  entry, one multiply-add makes the code, 8-byte stores are fully coalesced.  Three
+//                  forms: plain (every start has a code), masked (contig seams: the invalid-start mask
+//                  predicates the store and compacts the index), general (64-bit care, colliding
+//                  minimizers -> fallback_kmer_order, partitioned_mphf.cpp:308-313; several chunks).
 //
 // Every k-mer's code is a pure function of its own k bases, so tiles only share
 // k-1 bases of read overlap and nothing else.
+//
+// Code size matters here: the I-cache holds 32 KB per SM and the warps of an SM sit in different
+// phases, so everything rare (tie re-runs, invalid-start rasterisation, general emit, fallback
+// k-mers, dirty marking) is __noinline__ and the D loop keeps only kProbes = 2 probes per lane in
+// flight (profiles/r01c_experiments.md).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
