@@ -77,6 +77,9 @@ constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
 #ifndef LPHB_MINB
 #define LPHB_MINB 5
 #endif
+#ifndef LPHB_MINB_WIDE
+#define LPHB_MINB_WIDE 4
+#endif
 #ifndef LPHB_EMIT_UNROLL
 #define LPHB_EMIT_UNROLL 8
 #endif
@@ -479,7 +482,7 @@ static __device__ __noinline__ void fallback_kmers(DevImage const& f, const uint
 // order, the offset of its minimizer inside the k-mer (one byte, b.codes reinterpreted), from which
 // the super-k-mer heads follow (scan_kernels.cu).  `f` then only carries k, m and the seed.
 template <int K, int M, bool kScan = false>
-__global__ void __launch_bounds__(kThreads, (Cfg<K, M>::E == 1 ? LPHB_MINB : 4))
+__global__ void __launch_bounds__(kThreads, (Cfg<K, M>::E == 1 ? LPHB_MINB : LPHB_MINB_WIDE))
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
               const __grid_constant__ TileArgs a) {
     using C = Cfg<K, M>;
@@ -697,12 +700,21 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                 uint64_t marks = 0;  // bit j: thread-local position j is the minimizer of one of my k-mers
                 if (agree == kPosMask) {
                     uint32_t pk[4];
+                    // starts without a code (contig seams) do not ask for their minimizer: in a batch of
+                    // short reads that is a fifth fewer probes
                     if constexpr (C::E == 1) {
+                        const uint32_t inv16 = tile_clean ? 0u : (s_invalid[lseg >> 5] >> (lseg & 16)) & 0xFFFFu;
                         uint32_t m32 = 0;
+                        if (inv16 == 0) {
 #pragma unroll
-                        for (int i = 0; i < kS; ++i) m32 |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+                            for (int i = 0; i < kS; ++i) m32 |= __funnelshift_l(0u, 1u, mn[i]);  // 1 << (mn & 31)
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kS; ++i)
+                                if (!((inv16 >> i) & 1u)) m32 |= __funnelshift_l(0u, 1u, mn[i]);
+                        }
                         marks = m32;
-                    } else {
+                    } else {  // (the wide-window kernel is at its code-size limit: every start marks)
 #pragma unroll
                         for (int i = 0; i < kS; ++i) marks |= uint64_t(1) << (mn[i] & kPosMask);
                     }
