@@ -108,6 +108,19 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
  * streaming batches does not pay allocation on every batch); this frees it.                      */
 int lphb_scan_release(int device);
 
+/* ---- build-p Part 2: sort by minimizer + classify ----------------------------------------------
+ * Replaces the sort of the mm_record_t stream by minimizer (external_memory_vector<mm_record_t>,
+ * src/partitioned_mphf.cpp:62-66) and minimizer::classify (src/minimizer.cpp:5-50; caller
+ * src/partitioned_mphf.cpp:86).  records = n_records packed 18-byte mm_record_t in any order.
+ * triplets receives packed 10-byte mm_triplet_t {u64 itself, u8 p1, u8 size}
+ * (include/constants.hpp:35-41), one per distinct minimizer in ascending minimizer order -
+ * {itself, p1, size} for a minimizer seen once, {itself, 0, 0} for one seen several times - i.e. the
+ * key stream PTHash consumes; ids receives the ids of all occurrences of the latter, ascending.
+ * n_triplets / n_ids are also set when returning LPHB_E_CAPACITY.                                 */
+int lphb_classify(int device, const void* records, uint64_t n_records, void* triplets,
+                  uint64_t triplets_capacity, uint64_t* n_triplets, uint64_t* ids,
+                  uint64_t ids_capacity, uint64_t* n_ids);
+
 /* ---- build-p Part 4: k-mers of colliding minimizers -----------------------------------------
  * Replaces the loop over minimizer::get_colliding_kmers (include/minimizer.hpp:172-319; caller
  * src/partitioned_mphf.cpp:120-129).  ids = ascending minimizer-occurrence ids (classify's second

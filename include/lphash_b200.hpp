@@ -57,6 +57,16 @@ struct mm_record_t {
 #pragma pack(pop)
 static_assert(sizeof(mm_record_t) == 18, "mm_record_t is the reference's packed 18-byte record");
 
+// include/constants.hpp:35-41
+#pragma pack(push, 2)
+struct mm_triplet_t {
+    uint64_t itself;
+    uint8_t p1;
+    uint8_t size;
+};
+#pragma pack(pop)
+static_assert(sizeof(mm_triplet_t) == 10, "mm_triplet_t is the reference's packed 10-byte triplet");
+
 namespace detail {
 [[noreturn]] inline void raise(const char* what, int rc) {
     throw std::runtime_error(std::string(what) + ": " + lphb_last_error() + " (code " +
@@ -169,6 +179,22 @@ template <class Accumulator>
     if (rc != LPHB_OK) detail::raise("lphash_b200::minimizer::from_string", rc);
     for (uint64_t i = 0; i < n_rec; ++i) accumulator.push_back(rec[i]);
     return n_kmers;
+}
+
+// Sort by minimizer + minimizer::classify (src/minimizer.cpp:5-50): unique minimizers in ascending
+// order as triplets ({itself, 0, 0} for minimizers seen several times) and the ascending ids of the
+// occurrences of the latter.  `records` may be in any order (scan order is fine).
+inline void classify(std::vector<mm_record_t> const& records, std::vector<mm_triplet_t>& unique_minimizers,
+                     std::vector<uint64_t>& colliding_minimizer_ids, int device = 0) {
+    const uint64_t n = records.size();
+    unique_minimizers.resize(n ? n : 1);
+    colliding_minimizer_ids.resize(n ? n : 1);
+    uint64_t nt = 0, ni = 0;
+    int rc = lphb_classify(device, records.data(), n, unique_minimizers.data(), n, &nt,
+                           colliding_minimizer_ids.data(), n, &ni);
+    if (rc != LPHB_OK) detail::raise("lphash_b200::minimizer::classify", rc);
+    unique_minimizers.resize(nt);
+    colliding_minimizer_ids.resize(ni);
 }
 
 // Frees the device workspace the two build-side calls keep between calls (call after the loop over

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_load_file",
            "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
-           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release"]
+           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify"]
 
 _lib = None
 
@@ -210,6 +210,22 @@ def scan_superkmers(bases, offsets, k: int, m: int, seed: int = 42, mm_count: in
     _check(lib().lphb_scan_superkmers(device, k, m, seed, bases.ctypes.data, offsets.ctypes.data, n,
                                       C.byref(mm), rec.ctypes.data, cap, C.byref(nrec), C.byref(nk)))
     return rec[: nrec.value], nk.value, mm.value
+
+
+TRIPLET_DTYPE = np.dtype([("itself", "<u8"), ("p1", "u1"), ("size", "u1")])  # mm_triplet_t
+
+
+def classify(records, device: int = 0):
+    """Sort by minimizer + minimizer::classify (/root/reference/src/minimizer.cpp:5-50).
+    Returns (triplets[TRIPLET_DTYPE] in ascending minimizer order, ascending colliding ids)."""
+    records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    n = len(records)
+    trip = np.empty(max(n, 1), dtype=TRIPLET_DTYPE)
+    ids = np.empty(max(n, 1), dtype=np.uint64)
+    nt, ni = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().lphb_classify(device, records.ctypes.data, n, trip.ctypes.data, n, C.byref(nt),
+                               ids.ctypes.data, n, C.byref(ni)))
+    return trip[: nt.value].copy(), ids[: ni.value].copy()
 
 
 def colliding_kmers(bases, offsets, k: int, m: int, ids, seed: int = 42, kmer_bits: int = 64,

@@ -236,3 +236,43 @@ def test_wide_windows_long_contigs_match_oracle(name, handles):
     got, got_off = f.query_batch(bases, offsets)
     assert np.array_equal(got_off, want_off)
     assert np.array_equal(got, want)
+
+
+# ---- sort by minimizer + classify ---------------------------------------------------------------
+
+def test_classify_matches_reference_golden(golden):
+    """GPU scan -> GPU classify == the reference's classify outputs (the key stream PTHash consumes)."""
+    rec, _, _ = api.scan_superkmers(golden.index_bases, golden.index_offsets, golden.k, golden.m)
+    trip, ids = api.classify(rec)
+    assert trip.dtype == golden.triplets.dtype
+    assert np.array_equal(trip, golden.triplets)
+    assert np.array_equal(ids, golden.coll_ids)
+
+
+def test_classify_random_records_match_oracle():
+    """Any record order; heavy duplication (groups of 1 .. many), extreme key values, empty input."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    for n, n_keys in [(0, 1), (1, 1), (2, 1), (1000, 40), (50000, 30000), (200000, 199000)]:
+        rec = np.zeros(n, dtype=api.RECORD_DTYPE)
+        keys = rng.integers(0, 1 << 62, size=max(n_keys, 1), dtype=np.uint64)
+        keys[0] = 0
+        keys[-1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        rec["itself"] = keys[rng.integers(0, len(keys), size=n)]
+        rec["id"] = rng.permutation(n).astype(np.uint64) * np.uint64(3)
+        rec["p1"] = rng.integers(0, 40, size=n)
+        rec["size"] = rng.integers(1, 41, size=n)
+        want_t, want_i = oracle.classify(rec)
+        got_t, got_i = api.classify(rec)
+        assert np.array_equal(got_t, want_t), n
+        assert np.array_equal(got_i, want_i), n
+
+
+def test_classify_capacity_error():
+    rec = np.zeros(10, dtype=api.RECORD_DTYPE)
+    rec["itself"] = np.arange(10)
+    rec["size"] = 1
+    trip = np.empty(3, dtype=api.TRIPLET_DTYPE)
+    ids = np.empty(3, dtype=np.uint64)
+    nt, ni = C.c_uint64(0), C.c_uint64(0)
+    rc = api.lib().lphb_classify(0, rec.ctypes.data, 10, trip.ctypes.data, 3, C.byref(nt), ids.ctypes.data, 3, C.byref(ni))
+    assert rc == api.E_CAPACITY and nt.value == 10 and ni.value == 0
