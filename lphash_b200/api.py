@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
                                        u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_colliding_kmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
                                        u64, i32, p, u64, C.POINTER(u64)]
+    L.lphb_classify.argtypes = [i32, p, u64, p, u64, C.POINTER(u64), p, u64, C.POINTER(u64)]
+    L.lphb_scan_release.argtypes = [i32]
     L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
     L.lphb_host_free.argtypes = [p]
     for name in EXPORTS:

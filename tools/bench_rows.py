@@ -10,7 +10,9 @@ each (kept under profiles/):
           genome with 1 % substitutions, half random (mixed member / non-member k-mers), against the
           config-2 index; parity against the oracle on a prefix
 
-    python tools/bench_rows.py [scan] [k63] [reads] [--kmers N] [--reads N]
+  classify  sort by minimizer + minimizer::classify (lphb_classify) over the scan's record stream
+
+    python tools/bench_rows.py [scan] [classify] [k63] [reads] [--kmers N] [--reads N]
 """
 from __future__ import annotations
 
@@ -207,6 +209,56 @@ def main():
                                        "peak_source": src, "note": "whole call incl. PCIe copies (no device-resident entry point)"},
                           "parity": [f"first {len(wrec)} records bit-exact vs the CPU oracle", "sum of record sizes == k-mer count"],
                           "cpu_baseline": cpu}), flush=True)
+
+    if "classify" in args.rows:
+        import ctypes as C
+        import torch
+        from oracle import oracle
+        k, m = 31, 20
+        bases, offsets = synth.unitigs(args.kmers, k, m)
+        rec, nk, mm = api.scan_superkmers(bases, offsets, k, m)  # the GPU scan's record stream, scan order
+        n = len(rec)
+        h_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).pin_memory()
+        h_trip = torch.empty(n * 10, dtype=torch.uint8).pin_memory()
+        h_ids = torch.empty(max(n // 8, 1024), dtype=torch.int64).pin_memory()
+        L = api.lib()
+
+        def call():
+            nt, ni = C.c_uint64(0), C.c_uint64(0)
+            rc = L.lphb_classify(0, h_rec.data_ptr(), n, h_trip.data_ptr(), n, C.byref(nt), h_ids.data_ptr(),
+                                 len(h_ids), C.byref(ni))
+            assert rc == 0, L.lphb_last_error()
+            return nt.value, ni.value
+
+        call()
+        times = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            nt, ni = call()
+            times.append(time.perf_counter() - t0)
+        secs = float(np.mean(times))
+        t0 = time.perf_counter()
+        want_t, want_i = oracle.classify(rec)
+        cpu_secs = time.perf_counter() - t0
+        got_t = h_trip.numpy()[: nt * 10].view(api.TRIPLET_DTYPE)
+        got_i = h_ids.numpy()[:ni].view(np.uint64)
+        assert np.array_equal(got_t, want_t) and np.array_equal(got_i, want_i), "classify differs from the oracle"
+        peak, src = peak_gbs()
+        algo = 18 * n + 10 * nt + 8 * ni
+        print(json.dumps({"row": "classify", "metric": "build-p sort+classify records/sec", "value": n / secs,
+                          "unit": "records/s", "n_gpus": 1, "ms_per_step": secs * 1e3, "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": "records of the config-2 unitig scan (k=31 m=20) in scan order, sort by "
+                                                 "minimizer + classify through lphb_classify (pinned host buffers, mean of 5 calls)",
+                                     "records": int(n), "triplets": int(nt), "colliding_ids": int(ni)},
+                          "e2e": {"value": n / secs, "unit": "records/s", "h2d_bytes_per_step": 18 * n,
+                                  "d2h_bytes_per_step": 10 * nt + 8 * ni},
+                          "roofline": {"bound": "hbm", "achieved": algo / secs / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": algo / secs / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo),
+                                       "peak_source": src, "note": "whole call incl. PCIe copies and per-call allocations"},
+                          "parity": ["all triplets and colliding ids bit-exact vs the CPU oracle"],
+                          "cpu_baseline": {"value": n / cpu_secs, "unit": "records/s", "cores": 1, "kind": "port",
+                                           "sample": f"all {n} records, oracle classify (std::stable_sort + one pass), 1 thread"}}),
+              flush=True)
 
     if "k63" in args.rows:
         k, m, bits = 63, 24, 128
