@@ -121,6 +121,13 @@ int lphb_classify(int device, const void* records, uint64_t n_records, void* tri
                   uint64_t triplets_capacity, uint64_t* n_triplets, uint64_t* ids,
                   uint64_t ids_capacity, uint64_t* n_ids);
 
+/* Parts 1 + 2 in one call: lphb_scan_superkmers followed by lphb_classify with the record stream
+ * kept on the device (what mphf::build does between src/partitioned_mphf.cpp:62 and :86).        */
+int lphb_scan_classify(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                       const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count, void* triplets,
+                       uint64_t triplets_capacity, uint64_t* n_triplets, uint64_t* ids,
+                       uint64_t ids_capacity, uint64_t* n_ids, uint64_t* n_kmers);
+
 /* ---- build-p Part 4: k-mers of colliding minimizers -----------------------------------------
  * Replaces the loop over minimizer::get_colliding_kmers (include/minimizer.hpp:172-319; caller
  * src/partitioned_mphf.cpp:120-129).  ids = ascending minimizer-occurrence ids (classify's second

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_load_file",
            "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
-           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify"]
+           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify"]
 
 _lib = None
 
@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
                                        u64, i32, p, u64, C.POINTER(u64)]
     L.lphb_classify.argtypes = [i32, p, u64, p, u64, C.POINTER(u64), p, u64, C.POINTER(u64)]
     L.lphb_scan_release.argtypes = [i32]
+    L.lphb_scan_classify.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p, u64,
+                                     C.POINTER(u64), p, u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
     L.lphb_host_free.argtypes = [p]
     for name in EXPORTS:
@@ -228,6 +230,22 @@ def classify(records, device: int = 0):
     _check(lib().lphb_classify(device, records.ctypes.data, n, trip.ctypes.data, n, C.byref(nt),
                                ids.ctypes.data, n, C.byref(ni)))
     return trip[: nt.value].copy(), ids[: ni.value].copy()
+
+
+def scan_classify(bases, offsets, k: int, m: int, seed: int = 42, mm_count: int = 0, device: int = 0):
+    """from_string over the batch + sort + classify with the records kept on the device.
+    Returns (triplets, colliding ids, n_kmers, mm_count_out)."""
+    bases, offsets = _as_batch(bases, offsets)
+    n = len(offsets) - 1
+    cap = int(np.maximum(np.diff(offsets).astype(np.int64) - k + 1, 0).sum()) + 1
+    trip = np.empty(cap, dtype=TRIPLET_DTYPE)
+    ids = np.empty(cap, dtype=np.uint64)
+    mm = C.c_uint64(mm_count)
+    nt, ni, nk = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    _check(lib().lphb_scan_classify(device, k, m, seed, bases.ctypes.data, offsets.ctypes.data, n, C.byref(mm),
+                                    trip.ctypes.data, cap, C.byref(nt), ids.ctypes.data, cap, C.byref(ni),
+                                    C.byref(nk)))
+    return trip[: nt.value].copy(), ids[: ni.value].copy(), nk.value, mm.value
 
 
 def colliding_kmers(bases, offsets, k: int, m: int, ids, seed: int = 42, kmer_bits: int = 64,

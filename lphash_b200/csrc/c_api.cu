@@ -728,6 +728,52 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     return LPHB_OK;
 }
 
+// Sort by minimizer + classify of n records that are already on the device (stream s); results to host.
+int classify_device(const uint8_t* d_rec, uint64_t n, void* triplets, uint64_t triplets_capacity,
+                    uint64_t* n_triplets, uint64_t* ids, uint64_t ids_capacity, uint64_t* n_ids,
+                    cudaStream_t s) {
+    DevBuf key, key2, idx, idx2, flags, gslot, cslot, counts, tmp, trip, idu, ids_s;
+    struct Free {
+        std::vector<DevBuf*> v;
+        ~Free() {
+            for (DevBuf* d : v) d->release();
+        }
+    } fr{{&key, &key2, &idx, &idx2, &flags, &gslot, &cslot, &counts, &tmp, &trip, &idu, &ids_s}};
+    key.reserve(n * 8);
+    key2.reserve(n * 8);
+    idx.reserve(n * 4);
+    idx2.reserve(n * 4);
+    flags.reserve(n + 8);
+    gslot.reserve(n * 4);
+    cslot.reserve(n * 4);
+    counts.reserve(64);
+    const uint64_t tb = classify_tmp_bytes(n);
+    tmp.reserve(tb);
+    launch_classify_groups(d_rec, n, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<uint32_t>(),
+                           idx2.as<uint32_t>(), flags.as<uint8_t>(), gslot.as<uint32_t>(), cslot.as<uint32_t>(),
+                           counts.as<unsigned long long>(), tmp.p, tb, s);
+    unsigned long long h_counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(h_counts, counts.p, sizeof(h_counts), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    *n_triplets = h_counts[0];
+    *n_ids = h_counts[1];
+    if (h_counts[0] > triplets_capacity) return fail(LPHB_E_CAPACITY, "triplets buffer too small");
+    if (h_counts[1] > ids_capacity) return fail(LPHB_E_CAPACITY, "ids buffer too small");
+    if (!triplets || (h_counts[1] && !ids)) return fail(LPHB_E_ARG, "null output buffer");
+    trip.reserve(h_counts[0] * 10 + 64);
+    idu.reserve(h_counts[1] * 8 + 64);
+    ids_s.reserve(h_counts[1] * 8 + 64);
+    launch_classify_emit(d_rec, key2.as<uint64_t>(), idx2.as<uint32_t>(), flags.as<uint8_t>(),
+                         gslot.as<uint32_t>(), cslot.as<uint32_t>(), n, trip.as<uint8_t>(), idu.as<uint64_t>(),
+                         ids_s.as<uint64_t>(), h_counts[1], tmp.p, tb, s);
+    CK(cudaMemcpyAsync(triplets, trip.p, h_counts[0] * 10, cudaMemcpyDeviceToHost, s));
+    if (h_counts[1]) CK(cudaMemcpyAsync(ids, ids_s.p, h_counts[1] * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return LPHB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -778,52 +824,44 @@ int lphb_classify(int device, const void* records, uint64_t n_records, void* tri
         *n_triplets = 0;
         *n_ids = 0;
         if (n_records == 0) return LPHB_OK;
-        const uint64_t n = n_records;
-        DevBuf rec, key, key2, idx, idx2, flags, gslot, cslot, counts, tmp, trip, idu, ids_s;
+        DevBuf rec;
         struct Free {
-            std::vector<DevBuf*> v;
+            DevBuf* d;
             cudaStream_t s = nullptr;
             ~Free() {
-                for (DevBuf* d : v) d->release();
+                d->release();
                 if (s) cudaStreamDestroy(s);
             }
-        } fr{{&rec, &key, &key2, &idx, &idx2, &flags, &gslot, &cslot, &counts, &tmp, &trip, &idu, &ids_s}};
+        } fr{&rec};
         CK(cudaStreamCreateWithFlags(&fr.s, cudaStreamNonBlocking));
-        cudaStream_t s = fr.s;
-        rec.reserve(n * 18 + 64);
-        key.reserve(n * 8);
-        key2.reserve(n * 8);
-        idx.reserve(n * 4);
-        idx2.reserve(n * 4);
-        flags.reserve(n + 8);
-        gslot.reserve(n * 4);
-        cslot.reserve(n * 4);
-        counts.reserve(64);
-        const uint64_t tb = classify_tmp_bytes(n);
-        tmp.reserve(tb);
-        CK(cudaMemcpyAsync(rec.p, records, n * 18, cudaMemcpyHostToDevice, s));
-        launch_classify_groups(rec.as<uint8_t>(), n, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<uint32_t>(),
-                               idx2.as<uint32_t>(), flags.as<uint8_t>(), gslot.as<uint32_t>(),
-                               cslot.as<uint32_t>(), counts.as<unsigned long long>(), tmp.p, tb, s);
-        unsigned long long h_counts[2] = {0, 0};
-        CK(cudaMemcpyAsync(h_counts, counts.p, sizeof(h_counts), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(cudaGetLastError());
-        *n_triplets = h_counts[0];
-        *n_ids = h_counts[1];
-        if (h_counts[0] > triplets_capacity) return fail(LPHB_E_CAPACITY, "triplets buffer too small");
-        if (h_counts[1] > ids_capacity) return fail(LPHB_E_CAPACITY, "ids buffer too small");
-        if (!triplets || (h_counts[1] && !ids)) return fail(LPHB_E_ARG, "null output buffer");
-        trip.reserve(h_counts[0] * 10 + 64);
-        idu.reserve(h_counts[1] * 8 + 64);
-        ids_s.reserve(h_counts[1] * 8 + 64);
-        launch_classify_emit(rec.as<uint8_t>(), key2.as<uint64_t>(), idx2.as<uint32_t>(), flags.as<uint8_t>(),
-                             gslot.as<uint32_t>(), cslot.as<uint32_t>(), n, trip.as<uint8_t>(),
-                             idu.as<uint64_t>(), ids_s.as<uint64_t>(), h_counts[1], tmp.p, tb, s);
-        CK(cudaMemcpyAsync(triplets, trip.p, h_counts[0] * 10, cudaMemcpyDeviceToHost, s));
-        if (h_counts[1]) CK(cudaMemcpyAsync(ids, ids_s.p, h_counts[1] * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(cudaGetLastError());
+        rec.reserve(n_records * 18 + 64);
+        CK(cudaMemcpyAsync(rec.p, records, n_records * 18, cudaMemcpyHostToDevice, fr.s));
+        return classify_device(rec.as<uint8_t>(), n_records, triplets, triplets_capacity, n_triplets, ids,
+                               ids_capacity, n_ids, fr.s);
+    });
+}
+
+int lphb_scan_classify(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
+                       const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count, void* triplets,
+                       uint64_t triplets_capacity, uint64_t* n_triplets, uint64_t* ids,
+                       uint64_t ids_capacity, uint64_t* n_ids, uint64_t* n_kmers) {
+    if (!offsets || !mm_count || !n_triplets || !n_ids || !n_kmers) return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        std::lock_guard<std::mutex> lock(g_scan_mu);
+        ScanSession& S = scan_session(device);
+        uint64_t mm_out = *mm_count;
+        int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
+        if (rc != LPHB_OK) return rc;
+        *n_kmers = S.n_kmers;
+        *n_triplets = 0;
+        *n_ids = 0;
+        if (S.n_records) {  // the records never leave the device
+            rc = classify_device(S.records.as<uint8_t>(), S.n_records, triplets, triplets_capacity, n_triplets,
+                                 ids, ids_capacity, n_ids, S.s);
+            if (rc != LPHB_OK) return rc;
+        }
+        *mm_count = mm_out;
         return LPHB_OK;
     });
 }

@@ -276,3 +276,10 @@ def test_classify_capacity_error():
     nt, ni = C.c_uint64(0), C.c_uint64(0)
     rc = api.lib().lphb_classify(0, rec.ctypes.data, 10, trip.ctypes.data, 3, C.byref(nt), ids.ctypes.data, 3, C.byref(ni))
     assert rc == api.E_CAPACITY and nt.value == 10 and ni.value == 0
+
+
+def test_scan_classify_fused_matches_reference_golden(golden):
+    trip, ids, nk, mm = api.scan_classify(golden.index_bases, golden.index_offsets, golden.k, golden.m)
+    assert nk == int(golden.n_kmers) and mm == int(golden.mm_count)
+    assert np.array_equal(trip, golden.triplets)
+    assert np.array_equal(ids, golden.coll_ids)
