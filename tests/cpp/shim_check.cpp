@@ -74,6 +74,14 @@ int main(int argc, char** argv) {
             lb::minimizer::get_colliding_kmers(idx.bases + idx.offsets[c], idx.offsets[c + 1] - idx.offsets[c],
                                                uint32_t(k), uint32_t(m), 42, false, it, stop, mm2, coll);
         if (it != stop || mm2 != mm_count) throw std::logic_error("colliding-id stream not consumed");
+        // classify over the scan's stream must reproduce the id list the test handed in
+        std::vector<lb::mm_triplet_t> uniq;
+        std::vector<uint64_t> coll_ids;
+        lb::minimizer::classify(records, uniq, coll_ids);
+        if (coll_ids != ids) throw std::logic_error("classify: colliding ids differ");
+        for (size_t i = 1; i < uniq.size(); ++i)
+            if (!(uniq[i - 1].itself < uniq[i].itself)) throw std::logic_error("classify: triplets not strictly ascending");
+        lb::minimizer::release_workspace();
 
         std::ofstream out(argv[3], std::ios::binary);
         auto put = [&](uint64_t v) { out.write(reinterpret_cast<const char*>(&v), 8); };
@@ -85,6 +93,8 @@ int main(int argc, char** argv) {
         put(mm_count);
         put(coll.size());
         out.write(reinterpret_cast<const char*>(coll.data()), std::streamsize(coll.size() * sizeof(lb::kmer_t)));
+        put(uniq.size());
+        out.write(reinterpret_cast<const char*>(uniq.data()), std::streamsize(uniq.size() * sizeof(lb::mm_triplet_t)));
         std::printf("ok k=%u m=%u kmers=%llu codes=%zu records=%zu colliding=%zu\n", hf.get_k(), hf.get_m(),
                     (unsigned long long)hf.get_kmer_count(), codes.size(), records.size(), coll.size());
         return 0;

@@ -83,3 +83,7 @@ def test_shim_matches_reference_golden(tmp_path, name):
     words = g.bits // 64
     coll = np.frombuffer(raw, dtype="<u8", count=n * words, offset=pos).reshape(n, words)
     assert np.array_equal(coll, g.coll_kmers)
+    pos += 8 * n * words
+    n = u64()
+    trip = np.frombuffer(raw, dtype=g.triplets.dtype, count=n, offset=pos)
+    assert np.array_equal(trip, g.triplets)
