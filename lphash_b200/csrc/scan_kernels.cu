@@ -149,17 +149,19 @@ __global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanB
                                                    uint32_t* head_at) {
     __shared__ __align__(16) uint16_t s_rec[kEmitChunk * 9];
     __shared__ uint16_t s_list[kEmitChunk];
+    __shared__ uint64_t s_c0;
     const uint32_t m = b.m;
     const uint64_t n = b.n_kmers;
     for (uint64_t d0 = uint64_t(blockIdx.x) * kEmitChunk; d0 < n; d0 += uint64_t(gridDim.x) * kEmitChunk) {
         const uint64_t d1 = d0 + kEmitChunk < n ? d0 + kEmitChunk : n;
         const uint32_t r0 = rank[d0], r1 = rank[d1];
-        // contig of the chunk's first k-mer, once per chunk (same addresses in every thread); a record
-        // then walks forward from it (a chunk rarely spans more than a few contigs)
-        const uint64_t c0 = find_contig(b.code_off, b.n_contigs, d0);
+        // contig of the chunk's first k-mer, once per chunk; a record then walks forward from it (a chunk
+        // rarely spans more than a few contigs)
+        if (threadIdx.x == 0) s_c0 = find_contig(b.code_off, b.n_contigs, d0);
         for (uint64_t d = d0 + threadIdx.x; d < d1; d += blockDim.x)
             if (head[d]) s_list[rank[d] - r0] = uint16_t(d - d0);
         __syncthreads();
+        const uint64_t c0 = s_c0;
         for (uint32_t t = threadIdx.x; t < r1 - r0; t += blockDim.x) {
             const uint64_t d = d0 + s_list[t];
             // last contig whose first k-mer is at or before d (contigs without k-mers share their successor's offset)
@@ -171,8 +173,10 @@ __global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanB
             const char* s = b.bases + i + p1;
             uint64_t mm = 0;
 #pragma unroll
-            for (int j = 0; j < 31; ++j)
-                if (j < int(m)) mm = (mm << 2) | (nt4(uint8_t(s[j])) & 3u);
+            for (int j = 0; j < 31; ++j) {  // clean input only (a dirty batch was rejected before pass 2)
+                const uint32_t ch = uint8_t(s[j < int(m) ? j : 0]);
+                if (j < int(m)) mm = (mm << 2) | (((ch >> 1) ^ (ch >> 2)) & 3u);
+            }
             uint64_t e;  // next head
             if (t + 1 < r1 - r0) {
                 e = d0 + s_list[t + 1];
