@@ -728,17 +728,30 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     return LPHB_OK;
 }
 
+struct ClassifySession {
+    DevBuf rec, key, key2, idx, idx2, flags, gslot, cslot, counts, tmp, trip, idu, ids_s;
+    ~ClassifySession() {
+        for (DevBuf* d : {&rec, &key, &key2, &idx, &idx2, &flags, &gslot, &cslot, &counts, &tmp, &trip, &idu, &ids_s})
+            d->release();
+    }
+};
+ClassifySession* g_classify[64] = {};
+ClassifySession& classify_session(int device) {
+    if (device < 0 || device >= 64) throw std::invalid_argument("device index out of range");
+    if (!g_classify[device]) g_classify[device] = new ClassifySession();
+    return *g_classify[device];
+}
+
 // Sort by minimizer + classify of n records that are already on the device (stream s); results to host.
 int classify_device(const uint8_t* d_rec, uint64_t n, void* triplets, uint64_t triplets_capacity,
                     uint64_t* n_triplets, uint64_t* ids, uint64_t ids_capacity, uint64_t* n_ids,
                     cudaStream_t s) {
-    DevBuf key, key2, idx, idx2, flags, gslot, cslot, counts, tmp, trip, idu, ids_s;
-    struct Free {
-        std::vector<DevBuf*> v;
-        ~Free() {
-            for (DevBuf* d : v) d->release();
-        }
-    } fr{{&key, &key2, &idx, &idx2, &flags, &gslot, &cslot, &counts, &tmp, &trip, &idu, &ids_s}};
+    // workspace kept per device between calls (freed by lphb_scan_release); callers hold g_scan_mu
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    ClassifySession& cs = classify_session(dev);
+    DevBuf &key = cs.key, &key2 = cs.key2, &idx = cs.idx, &idx2 = cs.idx2, &flags = cs.flags, &gslot = cs.gslot,
+           &cslot = cs.cslot, &counts = cs.counts, &tmp = cs.tmp, &trip = cs.trip, &idu = cs.idu, &ids_s = cs.ids_s;
     key.reserve(n * 8);
     key2.reserve(n * 8);
     idx.reserve(n * 4);
@@ -806,10 +819,12 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
 int lphb_scan_release(int device) {
     return guarded([&]() -> int {
         std::lock_guard<std::mutex> lock(g_scan_mu);
-        if (device < 0 || device >= 64 || !g_scan[device]) return LPHB_OK;
+        if (device < 0 || device >= 64 || (!g_scan[device] && !g_classify[device])) return LPHB_OK;
         DeviceGuard g(device);
         delete g_scan[device];
         g_scan[device] = nullptr;
+        delete g_classify[device];
+        g_classify[device] = nullptr;
         return LPHB_OK;
     });
 }
@@ -824,15 +839,14 @@ int lphb_classify(int device, const void* records, uint64_t n_records, void* tri
         *n_triplets = 0;
         *n_ids = 0;
         if (n_records == 0) return LPHB_OK;
-        DevBuf rec;
+        std::lock_guard<std::mutex> lock(g_scan_mu);
+        DevBuf& rec = classify_session(device).rec;
         struct Free {
-            DevBuf* d;
             cudaStream_t s = nullptr;
             ~Free() {
-                d->release();
                 if (s) cudaStreamDestroy(s);
             }
-        } fr{&rec};
+        } fr;
         CK(cudaStreamCreateWithFlags(&fr.s, cudaStreamNonBlocking));
         rec.reserve(n_records * 18 + 64);
         CK(cudaMemcpyAsync(rec.p, records, n_records * 18, cudaMemcpyHostToDevice, fr.s));
