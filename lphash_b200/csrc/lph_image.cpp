@@ -1,5 +1,6 @@
 #include "lph_image.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace lphb {
@@ -194,7 +195,11 @@ void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits 
         e[D + i] = e[free_slots[i]];
     }
     img_.buckets.n = T;
-    if (max_base < (1ull << 30)) {
+    // 32-bit entries whenever every base fits 30 bits; LPHB_FORCE_WIDE_BUCKETS=1 (test hook) keeps the
+    // 64-bit form, which only indexes of >= 2^30 k-mers would otherwise exercise
+    const char* fw = getenv("LPHB_FORCE_WIDE_BUCKETS");
+    const bool force_wide = fw && fw[0] && fw[0] != '0';
+    if (max_base < (1ull << 30) && !force_wide) {
         std::vector<uint32_t> e32(T);
         for (uint64_t b = 0; b < T; ++b)
             e32[b] = uint32_t(e[b] >> 62) << 30 | uint32_t(e[b] & 0x3FFFFFFFull);  // same two flag bits on top

@@ -51,6 +51,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "device_mphf.cuh"
 #include "query_kernels.cuh"
 
@@ -70,12 +72,12 @@ constexpr int kStrips = 2;                     // passes per tile
 constexpr int kMinTile = kStrips * 29 * kS;    // smallest tile (bounds the set-up workspace)
 constexpr int kSlots = 1024;                   // positions a minimizer of the tile's k-mers can sit at (tile + < 64)
 constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
-// tuned on B200 (profiles/r01c_experiments.md): 2 probes per lane in flight, 5 CTAs per SM (102 registers, no spills)
+// tuned on B200 (profiles/r02_experiments.md): 4 CTAs of 4 warps per SM (128 registers), 3 probes per lane in flight
 #ifndef LPHB_PROBES
-#define LPHB_PROBES 2
+#define LPHB_PROBES 3
 #endif
 #ifndef LPHB_MINB
-#define LPHB_MINB 5
+#define LPHB_MINB 4
 #endif
 #ifndef LPHB_MINB_WIDE
 #define LPHB_MINB_WIDE 4
@@ -85,28 +87,31 @@ constexpr int kSlotWords = kSlots / 32;        // 32: one mask word per lane
 #endif
 constexpr int kProbes = LPHB_PROBES;           // probes a lane keeps in flight
 constexpr int kEmitUnroll = LPHB_EMIT_UNROLL;  // rows of the plain emit in flight
-constexpr int kGroups = 6;                     // 32-probe groups whose results a warp holds at once
-constexpr int kCap = 32 * kGroups;             // = 192 (the list index fits a byte)
-struct Entry {                                 // code of the k-mer at tile-local q = B + ns * q (mod 2^64)
-    uint32_t lo;                               // low word of B (the high word lives in s_hi)
-    int32_t ns;                                // -1: LEFT/MAXIMAL, +1: RIGHT/NONE, 0: colliding minimizer
+#ifndef LPHB_LISTCAP
+#define LPHB_LISTCAP 256
+#endif
+constexpr int kListCap = LPHB_LISTCAP;         // minimizer positions probed per D round-trip (chunk); tests build 32
+// What a probe leaves for the emit, indexed by the tile-local POSITION of the minimizer:
+// code of the k-mer at tile-local q = lo + nsq * q (32-bit; the high word is 0).  nsq = 0 marks an
+// entry the fast emit cannot use: lo = 0 colliding minimizer (every k-mer -> fallback_kmer_order),
+// lo = 1 the code does not fit 32 bits or may wrap (recomputed exactly in 64 bits, rare).
+struct Entry {
+    uint32_t lo;
+    int32_t nsq;                               // -1: LEFT/MAXIMAL, +1: RIGHT/NONE, 0: see above
 };
-constexpr int kPackedSlots = 68;               // packed words per tile: 62 + overlap + read-ahead of mmer_at
-constexpr int kRawBytes = 1088;                // ASCII bytes of one tile incl. overlap (<= 68 words), one TMA copy
+constexpr int kPackedSlots = 68;               // packed words per tile: 64 + zero read-ahead of mmer_at / win16
+constexpr int kRawBytes = 1024;                // ASCII bytes of one tile incl. overlap (64 words), one TMA copy
 // per-warp shared memory (bytes)
-constexpr int kOffEnt = 0;                               // Entry[kCap]
-constexpr int kOffHi = kOffEnt + kCap * 8;               // u32[kCap]
-constexpr int kOffList = kOffHi + kCap * 4;              // u16[kCap]
-constexpr int kOffPos = kOffList + kCap * 2;             // u8[kSlots]
-constexpr int kOffRef = kOffPos + kSlots;                // u8[kSlots]
-constexpr int kOffMin = kOffRef + kSlots;                // u32[32] minimizer-position mask
-constexpr int kOffFb = kOffMin + 128;                    // u32[32] fallback k-mers
+constexpr int kOffEnt = 0;                               // Entry[kSlots], by minimizer position
+constexpr int kOffPos = kOffEnt + kSlots * 8;            // u8[kSlots]  per k-mer start: thread-local minimizer position
+constexpr int kOffList = kOffPos + kSlots;               // u16[kListCap] minimizer positions of the chunk
+constexpr int kOffMin = kOffList + kListCap * 2;         // u32[32] minimizer-position mask
+constexpr int kOffFb = kOffMin + 128;                    // u32[32] k-mers that need the slow path
 constexpr int kOffInv = kOffFb + 128;                    // u32[32] invalid starts
-constexpr int kOffWpre = kOffInv + 128;                  // u16[32] marked positions before mask word
-constexpr int kOffInvPre = kOffWpre + 64;                // u16[32] invalid starts before mask word
+constexpr int kOffInvPre = kOffInv + 128;                // u16[32] invalid starts before mask word
 constexpr int kOffPacked = kOffInvPre + 64;              // u32[kPackedSlots]
-constexpr int kOffRaw = (kOffPacked + kPackedSlots * 4 + 15) / 16 * 16;  // 2 x kRawBytes (TMA destinations)
-constexpr int kOffBar = kOffRaw + 2 * kRawBytes;         // 2 mbarriers
+constexpr int kOffRaw = (kOffPacked + kPackedSlots * 4 + 15) / 16 * 16;  // kRawBytes (TMA destination)
+constexpr int kOffBar = kOffRaw + kRawBytes;             // mbarrier
 constexpr int kWarpBytes = kOffBar + 16;
 constexpr int kSmemBytes = kWarps * kWarpBytes;
 static_assert(kSlotWords == 32 && kWarpBytes % 16 == 0 && kOffRaw % 16 == 0 && kRawBytes % 16 == 0, "per-warp layout");
@@ -125,19 +130,19 @@ struct TileArgs {
     uint32_t n_tiles;
 };
 
-// 4 ASCII bytes -> 8 bits of 2-bit codes, byte 0 in the top 2 bits.  (x>>1 ^ x>>2) & 3 maps
+// 4 ASCII bytes -> 2-bit codes in the low bits of each byte.  (x>>1 ^ x>>2) & 3 maps
 // A,a->0 C,c->1 G,g->2 T,t,U,u->3 (src/constants.cpp:5-13 for the valid bytes).
 __device__ __forceinline__ uint32_t codes4(uint32_t x) { return ((x >> 1) ^ (x >> 2)) & 0x03030303u; }
-__device__ __forceinline__ uint32_t pack4(uint32_t y) { return (y * 0x40100401u) >> 24; }
-// nonzero iff one of the 4 bytes is not in {A,C,G,T,U,a,c,g,t,u}: rebuild the canonical upper-case
-// letter of each code with a byte permute and compare (T and U both map to 3: two tables).
+// codes of 4 bytes -> 8 bits, byte 0 in the top 2 bits, left in the TOP byte of the product
+__device__ __forceinline__ uint32_t pack4_top(uint32_t y) { return y * 0x40100401u; }
+// nonzero iff one of the 4 bytes is not in {A,C,G,T,a,c,g,t}: rebuild the canonical upper-case letter
+// of each code with a byte permute and compare.  U/u also come out nonzero here: the (out-of-line,
+// exact) slow check that follows accepts them, so RNA input is only slower, not different.
 __device__ __forceinline__ uint32_t bad4(uint32_t x, uint32_t y) {
     uint32_t z = y | (y >> 4);
-    uint32_t sel = __byte_perm(z, 0u, 0x4420u);  // nibble i = code of byte i
+    uint32_t sel = __byte_perm(z, 0u, 0x4420u);       // nibble i = code of byte i
     uint32_t c1 = __byte_perm(0x54474341u, 0u, sel);  // "ACGT"[code]
-    uint32_t c2 = __byte_perm(0x55474341u, 0u, sel);  // "ACGU"[code]
-    uint32_t u = x & 0xDFDFDFDFu;
-    return (u ^ c1) & (u ^ c2);
+    return (x & 0xDFDFDFDFu) ^ c1;
 }
 
 // flag the contig of every in-range non-ACGT byte of a 16-byte word (rare; out of line)
@@ -156,11 +161,6 @@ static __device__ __noinline__ void mark_dirty(DevBatch const& b, uint4 v, int64
             b.dirty[lo] = 1;
         }
     }
-}
-
-// code of a k-mer whose minimizer collides: fallback_kmer_order (rare; out of line)
-static __device__ __noinline__ uint64_t fallback_code(DevImage const& f, uint64_t klo, uint64_t khi) {
-    return f.collision_base + fallback_order(f, klo, khi);
 }
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
@@ -204,23 +204,45 @@ struct Cfg {
     static constexpr int Tile = kStrips * Strip;             // k-mer starts per (warp) tile
     static constexpr int MaskWords = Tile / 32;              // words of the invalid-start mask
     static constexpr int PosBits = E == 1 ? 5 : 6;           // thread-local minimizer position field of a key
-    static constexpr int TileWords = Tile / 16 + NW;         // 16-byte words staged per tile
+    static constexpr int TileWords = (Tile + K - 1 + 15) / 16;  // 16-byte words staged per tile
     static_assert(W >= 1 && E <= 3 && Tile >= kMinTile, "tiled kernel: window must fit three shuffle hops");
     static_assert(NH <= (1 << PosBits), "thread-local minimizer positions must fit the key's position field");
     static_assert(Tile % 32 == 0 && Tile + (E == 1 ? 32 : 64) <= kSlots, "mask words: one per lane");
     static_assert(M <= 31 && K <= 63, "k, m out of range");
-    static_assert(TileWords + 2 <= kPackedSlots && TileWords * 16 <= kRawBytes, "tile must fit its buffers");
+    static_assert(TileWords <= 64 && TileWords * 16 <= kRawBytes, "tile must fit its buffers");
+    static_assert(Tile / 16 + NW + 2 <= kPackedSlots, "packed read-ahead must stay inside the zero tail");
 };
 
-// a * 0xc6a4a7935bd1e995 mod 2^64 in three multiply-adds (IMAD.WIDE + 2 IMAD, all on the FMA pipe)
-__device__ __forceinline__ uint64_t mul_murmur(uint32_t lo, uint32_t hi) {
-    uint64_t w = uint64_t(lo) * 0x5bd1e995u;
-    uint32_t h = uint32_t(w >> 32);
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(lo), "r"(0xc6a4a793u));
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h) : "r"(hi), "r"(0x5bd1e995u));
-    return (uint64_t(h) << 32) | uint32_t(w);
+// (hi:lo) * 0xc6a4a7935bd1e995 mod 2^64 in three multiply-adds (IMAD.WIDE + 2 IMAD, all on the FMA pipe)
+__device__ __forceinline__ void mul_murmur(uint32_t lo, uint32_t hi, uint32_t& rlo, uint32_t& rhi) {
+    asm("{\n"
+        ".reg .u64 w;\n"
+        ".reg .u32 t;\n"
+        "mul.wide.u32 w, %2, 0x5bd1e995;\n"
+        "mov.b64 {%0, t}, w;\n"
+        "mad.lo.u32 t, %2, 0xc6a4a793, t;\n"
+        "mad.lo.u32 %1, %3, 0x5bd1e995, t;\n"
+        "}"
+        : "=r"(rlo), "=r"(rhi)
+        : "r"(lo), "r"(hi));
 }
-__device__ __forceinline__ uint64_t mul_murmur(uint64_t a) { return mul_murmur(uint32_t(a), uint32_t(a >> 32)); }
+// high word only of the same product (IMAD.HI + 2 IMAD)
+__device__ __forceinline__ uint32_t mul_murmur_hi(uint32_t lo, uint32_t hi) {
+    return __umulhi(lo, 0x5bd1e995u) + lo * 0xc6a4a793u + hi * 0x5bd1e995u;
+}
+// top 32 bits of MurmurHash2-64(v, seed) (device_mphf.cuh: murmur64; h0 = seed ^ 8*M): the final
+// h ^= h >> 47 cannot change them, and x ^= x >> 47 only touches the low word (x >> 47 has 17 bits)
+__device__ __forceinline__ uint32_t murmur_top32(uint32_t v_lo, uint32_t v_hi, uint32_t h0_lo, uint32_t h0_hi) {
+    uint32_t xl, xh;
+    mul_murmur(v_lo, v_hi, xl, xh);
+    xl ^= xh >> 15;
+    mul_murmur(xl, xh, xl, xh);
+    xl ^= h0_lo;
+    xh ^= h0_hi;
+    mul_murmur(xl, xh, xl, xh);
+    xl ^= xh >> 15;
+    return mul_murmur_hi(xl, xh);
+}
 
 // 16 bases starting at base t (compile-time after unrolling) of a thread's packed words
 template <int NW>
@@ -281,6 +303,30 @@ __device__ __forceinline__ uint64_t mmer_at(const uint32_t* s_packed, int g) {
     return ((uint64_t(hi) << 32) | lo) >> (64 - 2 * M);
 }
 
+// k-mer starting at tile-local base g as {lo, hi} words of kmer_t (first base most significant,
+// include/partitioned_mphf.hpp:108-109)
+template <int K, int NW>
+__device__ __forceinline__ void kmer_at(const uint32_t* s_packed, int g, uint64_t& klo, uint64_t& khi) {
+    const int wi = g >> 4, sh2 = (g & 15) * 2;
+    uint32_t x[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
+    uint32_t y[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], sh2);
+    // y[0..3] = 128-bit window starting at base g (y[0] most significant)
+    const uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
+    if constexpr (K <= 32) {
+        klo = top >> (64 - 2 * K);
+        khi = 0;
+        (void)bot;
+    } else {
+        constexpr int sh = 128 - 2 * K;  // 2..62
+        klo = (bot >> sh) | (top << (64 - sh));
+        khi = top >> sh;
+    }
+}
+
 // Exact minimizer offsets of the 16 k-mers starting at tile-local base g0, from the full 64-bit
 // hashes (strict '<' keeps the leftmost on ties: partitioned_mphf.hpp:124,152,159).  Taken only by
 // threads whose 27-bit keys tied; out of line.  Returns the mask of minimizer positions.
@@ -303,25 +349,24 @@ static __device__ __noinline__ uint64_t exact_strip(const uint32_t* s_packed, in
     return marks;
 }
 
-// Codes of the k-mers of a tile, position-parallel: lane l handles k-mers l, l+32, ...; two byte
-// loads find the entry of the k-mer's minimizer, code = B + ns * q, coalesced 8-byte stores.
+// Codes of the k-mers of a tile, position-parallel: lane l handles k-mers l, l+32, ...; one byte
+// load gives the position of the k-mer's minimizer, one 8-byte load its entry (the table is indexed
+// by position), code = lo + nsq * q, coalesced 8-byte streaming stores.
 //
-// Plain form, for a tile whose 992 starts all yield a code, whose entries share the high word
-// `hi` of B and cannot carry out of the low word (1024 <= lo < 2^32 - 1024), with no colliding
-// minimizer and a single chunk: one 32-bit multiply-add per code.
+// Plain form, for a tile whose starts all yield a code and whose entries are all regular (32-bit,
+// no colliding minimizer): one 32-bit multiply-add per code.
 template <int kTile>
-__device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
-                                           const Entry* s_ent, uint32_t hi, uint64_t* out_tile) {
+__device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const Entry* s_ent, uint64_t* out_tile) {
     const uint8_t* pos_l = s_pos + lane;
-    const uint8_t* ref_l = s_ref + (lane & 16);
+    const unsigned char* ent_l = reinterpret_cast<const unsigned char*>(s_ent + (lane & 16));
     uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
 #pragma unroll kEmitUnroll
     for (int r = 0; r < kTile / 32; ++r) {
-        const int mp = int(pos_l[r * 32]) + r * 32;  // (+ lane & 16) tile-local position of the minimizer
-        const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
+        // s_pos holds the minimizer's position relative to the owning thread's first start (q & ~15)
+        const int2 e = *reinterpret_cast<const int2*>(ent_l + (uint32_t(pos_l[r * 32]) * 8u + r * 256));
         uint32_t lo;
         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
-        __stcs(o + r * 32, make_uint2(lo, hi));
+        __stcs(o + r * 32, make_uint2(lo, 0u));
     }
 }
 
@@ -329,36 +374,28 @@ __device__ __forceinline__ void emit_plain(int lane, const uint8_t* s_pos, const
 // seams: every tile of a batch of short reads): the (warp-uniform) word of the invalid-start mask
 // predicates the store and compacts the output index.
 template <int kTile>
-__device__ __forceinline__ void emit_masked(int lane, const uint8_t* s_pos, const uint8_t* s_ref,
-                                            const Entry* s_ent, uint32_t hi, const uint32_t* s_invalid,
-                                            const uint16_t* s_invpre, uint64_t* out_tile) {
+__device__ __forceinline__ void emit_masked(int lane, const uint8_t* s_pos, const Entry* s_ent,
+                                            const uint32_t* s_invalid, const uint16_t* s_invpre, uint64_t* out_tile) {
     const uint8_t* pos_l = s_pos + lane;
-    const uint8_t* ref_l = s_ref + (lane & 16);
+    const unsigned char* ent_l = reinterpret_cast<const unsigned char*>(s_ent + (lane & 16));
     const uint32_t lt = (1u << lane) - 1u;
     uint2* o = reinterpret_cast<uint2*>(out_tile + lane);
 #pragma unroll 2
     for (int r = 0; r < kTile / 32; ++r) {
         const uint32_t mw = s_invalid[r];  // uniform in the warp
-        const int mp = int(pos_l[r * 32]) + r * 32;
-        const int2 e = *reinterpret_cast<const int2*>(s_ent + ref_l[mp]);
+        const int2 e = *reinterpret_cast<const int2*>(ent_l + (uint32_t(pos_l[r * 32]) * 8u + r * 256));
         uint32_t lo;
         asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(lo) : "r"(e.y), "r"(lane + r * 32), "r"(e.x));
-        if (!((mw >> lane) & 1u)) __stcs(o + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), make_uint2(lo, hi));
+        if (!((mw >> lane) & 1u)) __stcs(o + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), make_uint2(lo, 0u));
     }
 }
 
-// General form.  Per group of 32 starts the (warp-uniform) word of the invalid-start mask tells
-// whether starts without a code (contig seams) must be skipped and the output index compacted;
-// k-mers of colliding minimizers are flagged in s_fbmask; kChunked (more than kCap minimizers):
-// entries outside [i0, i1) are left to their own chunk.
-template <int kTile, bool kChunked>
-static __device__ __noinline__ void emit_general(int lane, uint32_t i0, uint32_t i1,
-                                             const uint8_t* s_pos, const uint8_t* s_ref,
-                                             const uint32_t* s_minmask, const uint16_t* s_wpre,
-                                             const Entry* s_ent, const uint32_t* s_hi,
-                                             uint32_t* s_fbmask,
-                                             const uint32_t* s_invalid, const uint16_t* s_invpre,
-                                             uint64_t* out) {
+// General form, for a tile with an entry the fast forms cannot use (nsq == 0): regular k-mers as
+// above, the others are flagged in s_fbmask and finished by slow_kmers.  Out of line.
+template <int kTile>
+static __device__ __noinline__ void emit_general(int lane, const uint8_t* s_pos, const Entry* s_ent,
+                                                 uint32_t* s_fbmask, const uint32_t* s_invalid,
+                                                 const uint16_t* s_invpre, uint64_t* out) {
     const int lane16 = lane & 16;
     const uint32_t lt = (1u << lane) - 1u;
     uint64_t* out_l = out + lane;
@@ -366,25 +403,14 @@ static __device__ __noinline__ void emit_general(int lane, uint32_t i0, uint32_t
     for (int r = 0; r < kTile / 32; ++r) {
         const int q = lane + r * 32;
         const uint32_t mw = s_invalid[r];  // uniform in the warp
-        if ((mw >> lane) & 1u) continue;
-        const int mp = int(s_pos[q]) + lane16 + r * 32;  // tile-local position of q's minimizer
-        uint32_t idx;
-        if (kChunked) {  // global list index of position mp: rank among the marked positions
-            idx = s_wpre[mp >> 5] + __popc(s_minmask[mp >> 5] & ((1u << (mp & 31)) - 1u));
-            if (idx < i0 || idx >= i1) continue;
-            idx -= i0;
-        } else {
-            idx = s_ref[mp];
-        }
-        const Entry e = s_ent[idx];
-        if (e.ns == 0) {  // colliding minimizer: needs the k-mer itself
-            atomicOr(&s_fbmask[r], 1u << lane);
-            continue;
-        }
-        const uint64_t B = (uint64_t(s_hi[idx]) << 32) | e.lo;
-        const uint64_t code = B + uint64_t(int64_t(e.ns) * int64_t(q));
-        __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), code);
+        const bool ok = !((mw >> lane) & 1u);
+        const Entry e = s_ent[ok ? int(s_pos[q]) + lane16 + r * 32 : 0];
+        const uint32_t slow = __ballot_sync(0xFFFFFFFFu, ok && e.nsq == 0);
+        if (lane == 0) s_fbmask[r] = slow;
+        if (ok && e.nsq != 0)
+            __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), uint64_t(e.lo + uint32_t(e.nsq * q)));
     }
+    __syncwarp();
 }
 
 // k-mer starts of a tile that produce no code (contig seams, short contigs, positions outside
@@ -435,45 +461,37 @@ static __device__ __noinline__ void mark_invalid(DevBatch const& b, uint32_t* s_
     __syncwarp();
 }
 
-// Colliding minimizers: every k-mer of the run goes through fallback_kmer_order
-// (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134).  Lane l takes bit l of every mask
-// word, so the consecutive k-mers of a run spread over the lanes and their (dependent, uncached)
-// gathers overlap.  Rare: out of line.
+// The k-mers the fast emit left out (s_fbmask), one lane per k-mer:
+//   * colliding minimizer (entry lo == 0): code = collision base + fallback_kmer_order(k-mer)
+//     (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134);
+//   * code outside 32 bits (entry lo == 1): the probe is redone and evaluated in 64 bits, mod 2^64
+//     like the reference (partitioned_mphf.cpp:337; non-members may underflow, SURVEY.md E1 vii).
+// Lane l takes bit l of every mask word, so the consecutive k-mers of a run spread over the lanes
+// and their (dependent, uncached) gathers overlap.  Rare: out of line.
 template <int K, int M, int kTile>
-static __device__ __noinline__ void fallback_kmers(DevImage const& f, const uint32_t* s_packed, uint32_t* s_fbmask,
-                                                   const uint32_t* s_invalid, const uint16_t* s_invpre, int lane,
-                                                   uint64_t* out) {
+static __device__ __noinline__ void slow_kmers(DevImage const& f, const uint32_t* s_packed, const uint8_t* s_pos,
+                                               const Entry* s_ent, const uint32_t* s_fbmask,
+                                               const uint32_t* s_invalid, const uint16_t* s_invpre, int lane,
+                                               uint64_t* out) {
     constexpr int NW = Cfg<K, M>::NW, kMaskWords = kTile / 32;
 #pragma unroll 1
     for (int r = 0; r < kMaskWords; ++r) {
         const uint32_t fw = s_fbmask[r];  // uniform
         if (!((fw >> lane) & 1u)) continue;
         const int g = r * 32 + lane;
-        const int wi = g >> 4, sh2 = (g & 15) * 2;
-        uint32_t x[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) x[j] = (j <= NW) ? s_packed[min(wi + j, kPackedSlots - 1)] : 0u;
-        uint32_t y[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) y[j] = __funnelshift_l(x[j + 1], x[j], sh2);
-        // y[0..3] = 128-bit window starting at base g (y[0] most significant)
-        uint64_t top = (uint64_t(y[0]) << 32) | y[1], bot = (uint64_t(y[2]) << 32) | y[3];
-        uint64_t klo, khi;
-        if constexpr (K <= 32) {
-            klo = top >> (64 - 2 * K);
-            khi = 0;
-            (void)bot;
+        const int mp = int(s_pos[g]) + (lane & 16) + r * 32;  // tile-local position of g's minimizer
+        uint64_t code;
+        if (s_ent[mp].lo == 0u) {
+            uint64_t klo, khi;
+            kmer_at<K, NW>(s_packed, g, klo, khi);
+            code = f.collision_base + fallback_order(f, klo, khi);
         } else {
-            constexpr int sh = 128 - 2 * K;  // 2..62
-            klo = (bot >> sh) | (top << (64 - sh));
-            khi = top >> sh;
+            const Probe pr = probe_minimizer(f, mmer_at<M>(s_packed, mp));
+            code = probe_hval(pr, uint32_t(mp - g));
         }
         const uint32_t mw = s_invalid[r];
-        const int oidx = g - int(s_invpre[r] + __popc(mw & ((1u << lane) - 1u)));
-        out[oidx] = fallback_code(f, klo, khi);
+        out[g - int(s_invpre[r] + __popc(mw & ((1u << lane) - 1u)))] = code;
     }
-    __syncwarp();
-    if (lane < kMaskWords) s_fbmask[lane] = 0;
     __syncwarp();
 }
 
@@ -493,21 +511,18 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = smem_raw + warp * kWarpBytes;
-    Entry* s_ent = reinterpret_cast<Entry*>(mine + kOffEnt);          // per probe (list index)
-    uint32_t* s_hi = reinterpret_cast<uint32_t*>(mine + kOffHi);      // per probe: high word of B
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(mine + kOffList);  // minimizer positions of the chunk
+    Entry* s_ent = reinterpret_cast<Entry*>(mine + kOffEnt);          // per minimizer position
     uint8_t* s_pos = mine + kOffPos;                                  // per k-mer: thread-local minimizer position
-    uint8_t* s_ref = mine + kOffRef;                                  // per position: chunk-local list index
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(mine + kOffList);  // minimizer positions of the chunk
     uint32_t* s_minmask = reinterpret_cast<uint32_t*>(mine + kOffMin);  // bit p: position p is some k-mer's minimizer
-    uint32_t* s_fbmask = reinterpret_cast<uint32_t*>(mine + kOffFb);    // bit q: k-mer q needs fallback_kmer_order
+    uint32_t* s_fbmask = reinterpret_cast<uint32_t*>(mine + kOffFb);    // bit q: k-mer q goes through slow_kmers
     uint32_t* s_invalid = reinterpret_cast<uint32_t*>(mine + kOffInv);  // bit q: k-mer start q produces no code
-    uint16_t* s_wpre = reinterpret_cast<uint16_t*>(mine + kOffWpre);    // marked positions before mask word
     uint16_t* s_invpre = reinterpret_cast<uint16_t*>(mine + kOffInvPre);  // invalid starts before mask word
     uint32_t* s_packed = reinterpret_cast<uint32_t*>(mine + kOffPacked);  // 2-bit bases of the tile
-    unsigned char* s_rawbuf = mine + kOffRaw;                         // 2 x raw ASCII (TMA destinations)
+    unsigned char* s_raw = mine + kOffRaw;                            // raw ASCII of the tile (TMA destination)
     uint64_t* s_mbar = reinterpret_cast<uint64_t*>(mine + kOffBar);
 
-    const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
+    const int64_t end = int64_t(b.end_base);
     const uint32_t n_warps = gridDim.x * kWarps;
     uint32_t tile = blockIdx.x * kWarps + warp;
     // bytes of tile t that exist (whole 16-byte words up to the one holding the last base)
@@ -519,15 +534,15 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     };
     const uint64_t stream_pol = l2_stream_policy();
     if (lane == 0) {
-        mbar_init(&s_mbar[0], 1);
-        mbar_init(&s_mbar[1], 1);
+        mbar_init(s_mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (tile < a.n_tiles) {  // first tile of this warp
             const uint32_t nb = tile_bytes(tile);
-            mbar_expect_tx(&s_mbar[0], nb);
-            tma_load_1d(s_rawbuf, a.abase + int64_t(tile) * kTile, nb, &s_mbar[0], stream_pol);
+            mbar_expect_tx(s_mbar, nb);
+            tma_load_1d(s_raw, a.abase + int64_t(tile) * kTile, nb, s_mbar, stream_pol);
         }
     }
+    if (lane < kPackedSlots - 64) s_packed[64 + lane] = 0;  // read-ahead tail, never written again
     __syncwarp();
     TileRec rec{};
     if (tile < a.n_tiles) {
@@ -537,52 +552,52 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         rec.clean = v.w;
     }
     const uint64_t h0 = f.mm_seed ^ (8 * kMurmurM);
+    const uint32_t h0_lo = uint32_t(h0), h0_hi = uint32_t(h0 >> 32);
     uint32_t keymask;  // ~position mask held in a register so that (hash & mask) | position is one LOP3
     asm volatile("mov.u32 %0, %1;" : "=r"(keymask) : "n"(~((1u << C::PosBits) - 1u)));
 
     uint32_t iter = 0;
 #pragma unroll 1
     for (; tile < a.n_tiles; tile += n_warps, ++iter) {
-        const uint32_t buf = iter & 1u;
-        const unsigned char* s_raw = s_rawbuf + buf * kRawBytes;
         const int64_t T0 = a.pos0 + int64_t(tile) * kTile;  // stream position of tile-local 0
         const TileRec cur = rec;
 
         // ------------------------------------------------------------ A: stage + pack ------------
-        // prefetch this warp's next tile into the other raw buffer (all lanes finished reading it
-        // one iteration ago) and its set-up record into registers; then wait for this tile's bytes
+        s_minmask[lane] = 0;
+        s_invalid[lane] = 0;
+        mbar_wait(s_mbar, iter & 1u);
+        const int n_words = int(tile_bytes(tile) >> 4);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int t = lane + 32 * it;
+            uint32_t word = 0;
+            if (t < n_words) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_raw + t * 16);
+                const uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
+                // first base in the most significant bits (partitioned_mphf.hpp:106-108)
+                word = __byte_perm(__byte_perm(pack4_top(y1), pack4_top(y0), 0x7300),   // . . y1 y0 -> bytes 2,3
+                                   __byte_perm(pack4_top(y3), pack4_top(y2), 0x0073), 0x3254);
+                const uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
+                if (bad) mark_dirty(b, v, T0 + int64_t(t) * 16);  // rare
+            }
+            s_packed[t] = word;
+        }
+        __syncwarp();
+        // the raw bytes are consumed: fetch this warp's next tile into the same buffer (it lands while
+        // this tile is scanned and probed) and its set-up record into registers
         const uint32_t next = tile + n_warps;
         if (next < a.n_tiles) {
             if (lane == 0) {
                 const uint32_t nb = tile_bytes(next);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&s_mbar[buf ^ 1u], nb);
-                tma_load_1d(s_rawbuf + (buf ^ 1u) * kRawBytes, a.abase + int64_t(next) * kTile, nb,
-                            &s_mbar[buf ^ 1u], stream_pol);
+                mbar_expect_tx(s_mbar, nb);
+                tma_load_1d(s_raw, a.abase + int64_t(next) * kTile, nb, s_mbar, stream_pol);
             }
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.recs + next));
             rec.out = (uint64_t(v.y) << 32) | v.x;
             rec.c0 = v.z;
             rec.clean = v.w;
         }
-        s_minmask[lane] = 0;
-        s_fbmask[lane] = 0;
-        s_invalid[lane] = 0;
-        mbar_wait(&s_mbar[buf], (iter >> 1) & 1u);
-        const int n_words = int(tile_bytes(tile) >> 4);
-#pragma unroll 1
-        for (int t = lane; t < kPackedSlots; t += 32) {
-            uint32_t word = 0;
-            if (t < n_words) {
-                const uint4 v = *reinterpret_cast<const uint4*>(s_raw + t * 16);
-                uint32_t y0 = codes4(v.x), y1 = codes4(v.y), y2 = codes4(v.z), y3 = codes4(v.w);
-                word = (pack4(y0) << 24) | (pack4(y1) << 16) | (pack4(y2) << 8) | pack4(y3);
-                uint32_t bad = bad4(v.x, y0) | bad4(v.y, y1) | bad4(v.z, y2) | bad4(v.w, y3);
-                if (bad) mark_dirty(b, v, T0 + int64_t(t) * 16);  // rare
-            }
-            s_packed[t] = word;
-        }
-        __syncwarp();
 
         // k-mer starts that produce no code (contig seams, short contigs, positions outside
         // [first, end)) -> s_invalid; nothing to do when one contig covers the tile and k-1 more bases
@@ -625,15 +640,8 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                     v_lo = win16<NW>(wds, j + M - 16);
                     v_hi = win16<NW>(wds, j) >> (64 - 2 * M);
                 }
-                // MurmurHash2-64 (device_mphf.cuh: murmur64) up to its last multiply: the final
-                // h ^= h >> 47 cannot change the top 32 bits
-                uint64_t x = M <= 16 ? uint64_t(v_lo) * kMurmurM : mul_murmur(v_lo, v_hi);
-                x ^= x >> 47;
-                x = mul_murmur(x);
-                uint64_t h = mul_murmur(h0 ^ x);
-                h ^= h >> 47;
-                h = mul_murmur(h);
-                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(uint32_t(h >> 32)), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
+                const uint32_t top = murmur_top32(v_lo, v_hi, h0_lo, h0_hi);
+                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(key[j]) : "r"(top), "r"(keymask), "r"(uint32_t(j)));  // (h & mask) | j
             }
 
             uint32_t mn[kS];         // per k-mer: key of its minimizer (leftmost among equal key prefixes)
@@ -642,7 +650,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                 // W <= 17: the W-1 keys a thread lacks come from lane+1 (positions 16..); sliding
                 // minimum by sparse table
 #pragma unroll
-                for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j] + 16u, 1);
+                for (int j = 0; j < W - 1; ++j) key[kS + j] = __shfl_down_sync(0xFFFFFFFFu, key[j], 1) | 16u;
                 window_min<W, NH>(key, mn);
                 // same windows with the position bits complemented: the minimum is now the RIGHTMOST
                 // one among equal prefixes; both agree on every window <=> no two candidates tied
@@ -680,9 +688,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                 }
 #pragma unroll
                 for (int i = 0; i < kS; ++i) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int end = i + W - 1, e = end >> 4, c = end & 15;  // compile-time after unrolling
+                    const int wend = i + W - 1, e = wend >> 4, c = wend & 15;  // compile-time after unrolling
                     uint32_t acc = min(S[i], __shfl_down_sync(0xFFFFFFFFu, P[c], e) + 16u * e);
                     uint32_t racc = min(rS[i], __shfl_down_sync(0xFFFFFFFFu, rP[c], e) - 16u * e);
 #pragma unroll
@@ -759,9 +765,9 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             continue;
         }
 
-        // ------------------------------------------------------------ C: rank the minimizers ----
-        // lane l owns mask word l: list index of every marked position
-        const uint32_t my_word = s_minmask[lane];
+        // ------------------------------------------------------------ C: list the minimizers ----
+        // lane l owns mask word l; list slot of its first marked position = marked positions before it
+        uint32_t my_word = s_minmask[lane];
         const uint32_t n_mine = __popc(my_word);
         uint32_t inc = n_mine;
 #pragma unroll
@@ -770,35 +776,29 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
             if (lane >= o) inc += v;
         }
         const uint32_t n_min = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const uint32_t my_first = inc - n_mine;
-        s_wpre[lane] = uint16_t(my_first);
+        uint32_t my_next = inc - n_mine;  // list index of my next marked position
 
-        uint64_t* out = b.codes + cur.out;
-        const bool chunked = n_min > kCap;
-
-        // ------------------------------------------------------------ D + E ----------------------
-        for (uint32_t i0 = 0; i0 < n_min; i0 += kCap) {
-            const uint32_t i1 = i0 + kCap < n_min ? i0 + kCap : n_min;
-            {
-                uint32_t word = my_word, idx = my_first;
-                while (word) {
-                    int bit = __ffs(word) - 1;
-                    word &= word - 1;
-                    if (idx >= i0 && idx < i1) s_list[idx - i0] = uint16_t(lane * 32 + bit);
-                    ++idx;
-                }
+        // ------------------------------------------------------------ D: probe ---------------------
+        // one lane per distinct minimizer position, in chunks of kListCap (one chunk unless the window
+        // is tiny or the hashes of the tile descend); the entries go to s_ent[position]
+        bool special = false;
+        const DevPhf& P = f.minimizer_order;
+        const uint64_t keep = l2_keep_policy();
+        const bool wide = f.buckets.wide != 0;
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < n_min; i0 += kListCap) {
+            const uint32_t i1 = i0 + kListCap < n_min ? i0 + kListCap : n_min;
+            while (my_word && my_next < i1) {  // my marked positions that fall into this chunk
+                const int bit = 31 - __clz(my_word);  // (any order: the entry table is indexed by position)
+                my_word ^= 1u << bit;
+                s_list[my_next - i0] = uint16_t(lane * 32 + bit);
+                ++my_next;
             }
             __syncwarp();
-            // kProbes probes per lane in flight: the dependent gathers (hashed pilot -> bucket word)
-            // of different probes overlap instead of queueing up
-            bool special = false, have = false;
-            uint32_t hi0 = 0;
-            const DevPhf& P = f.minimizer_order;
-            const uint64_t keep = l2_keep_policy();
             const uint32_t n_chunk = i1 - i0;
             const uint32_t nu = (n_chunk + 31) >> 5;  // 32-probe groups in this chunk (uniform)
-            const int fsh = f.buckets.wide ? 62 : 30;
-            const uint64_t bmask = (uint64_t(1) << fsh) - 1;
+            // kProbes probes per lane in flight: the dependent gathers (hashed pilot -> bucket word)
+            // of different probes overlap instead of queueing up
 #pragma unroll 1
             for (uint32_t g0 = 0; g0 < nu; g0 += kProbes) {
                 const uint32_t ng = nu - g0;  // live groups of this round (uniform), >= 1
@@ -820,59 +820,79 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
 #ifdef LPHB_EXP_NOGATHER  // timing experiment only (wrong codes): no image reads
                     if (u < ng) hp[u] = h[u] + slot[u];
 #else
+#ifdef LPHB_EXP_SMALLTAB  // timing experiment only (wrong codes): gathers confined to an L2-resident corner
+                    if (u < ng) hp[u] = ldg_keep(P.pilot_hash + (slot[u] & 0x3FFFFu), keep);
+#else
                     if (u < ng) hp[u] = ldg_keep(P.pilot_hash + slot[u], keep);
 #endif
+#endif
                 // the bucket table is indexed by the raw table slot (free slots folded in at load time)
-                uint64_t word[kProbes];
+                uint32_t wlo[kProbes], whi[kProbes];
 #pragma unroll
                 for (int u = 0; u < kProbes; ++u) {
                     if (u < ng) {
+#ifdef LPHB_EXP_SMALLTAB
+                        const uint32_t ts = phf_table_slot(P, h[u] ^ hp[u]) & 0xFFFFFu;
+#else
                         const uint32_t ts = phf_table_slot(P, h[u] ^ hp[u]);
+#endif
 #ifdef LPHB_EXP_NOGATHER
-                        word[u] = (ts & 0x3FFFFFFFu) | 0x80000000u;
+                        wlo[u] = (ts & 0x3FFFFFFFu) | 0x80000000u;
+                        whi[u] = 0;
                         continue;
 #endif
-                        if (f.buckets.wide) word[u] = ldg_keep(reinterpret_cast<const uint64_t*>(f.buckets.entries) + ts, keep);
-                        else word[u] = ldg_keep(reinterpret_cast<const uint32_t*>(f.buckets.entries) + ts, keep);
+                        if (wide) {
+                            const uint64_t wv = ldg_keep(reinterpret_cast<const uint64_t*>(f.buckets.entries) + ts, keep);
+                            wlo[u] = uint32_t(wv);
+                            whi[u] = uint32_t(wv >> 32);
+                        } else {
+                            wlo[u] = ldg_keep(reinterpret_cast<const uint32_t*>(f.buckets.entries) + ts, keep);
+                            whi[u] = 0;
+                        }
                     }
                 }
-                // bucket word -> {B, ns}: hval = base + slope * (bp - q) = (base + slope * bp) + (-slope) * q
+                // bucket word -> entry: hval(q) = base + slope * (bp - q) = (base + slope * bp) - slope * q
 #pragma unroll
                 for (int u = 0; u < kProbes; ++u) {
                     const uint32_t li = lane + 32 * (g0 + u);
                     if (u < ng && li < n_chunk) {
-                        const uint32_t flags = uint32_t(word[u] >> fsh);  // bit 1: slope +1, bit 0: colliding
-                        const int32_t ns = (flags & 1u) ? 0 : ((flags & 2u) ? -1 : 1);
-                        const uint64_t B = (word[u] & bmask) - uint64_t(int64_t(ns) * bp[u]);
-                        const uint32_t lo = uint32_t(B), hi = uint32_t(B >> 32);
-                        if (!have) { hi0 = hi; have = true; }
-                        special |= ns == 0 || hi != hi0 || lo - 1024u >= 0xFFFFF800u;  // needs 64-bit care
-                        s_ent[li] = Entry{lo, ns};
-                        s_hi[li] = hi;
-                        s_ref[bp[u]] = uint8_t(li);
+                        // flags on top of the word: slope +1 (LEFT/MAXIMAL) | colliding; base below
+                        const uint32_t top = wide ? whi[u] : wlo[u];
+                        const uint32_t base = wide ? wlo[u] : (wlo[u] & 0x3FFFFFFFu);
+                        const int32_t nsq = (int32_t(top) >> 31) | 1;  // -slope: -1 if slope +1, else +1
+                        const bool colliding = (top & 0x40000000u) != 0;
+                        // regular <=> base + slope * o stays inside [0, 2^32) for every offset o <= k - m
+                        bool care = nsq > 0 ? base < uint32_t(K - M) : base > 0xFFFFFFFFu - uint32_t(K - M);
+                        if (wide) care |= (top & 0x3FFFFFFFu) != 0;
+#ifdef LPHB_TEST_CARE_BELOW  // test build: push regular entries through the exact 64-bit path too
+                        care |= base < uint32_t(LPHB_TEST_CARE_BELOW);
+#endif
+                        Entry e;
+                        if (colliding | care) {
+                            e.lo = colliding ? 0u : 1u;
+                            e.nsq = 0;
+                            special = true;
+                        } else {
+                            e.lo = base - uint32_t(nsq * bp[u]);
+                            e.nsq = nsq;
+                        }
+                        s_ent[bp[u]] = e;
                     }
                 }
             }
-            // plain emit needs: every entry of the tile shares lane 0's high word and cannot carry, no
-            // colliding minimizer, no start without a code, one chunk
-            const uint32_t hi_warp = __shfl_sync(0xFFFFFFFFu, hi0, 0);
-            special |= have && hi0 != hi_warp;
-            const bool simple = !chunked && !__any_sync(0xFFFFFFFFu, special);
-            const bool plain = simple && !tile_has_invalid;
             __syncwarp();
-            if (plain) emit_plain<kTile>(lane, s_pos, s_ref, s_ent, hi_warp, out);
-            else if (simple) emit_masked<kTile>(lane, s_pos, s_ref, s_ent, hi_warp, s_invalid, s_invpre, out);
-            else if (!chunked) emit_general<kTile, false>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
-            else emit_general<kTile, true>(lane, i0, i1, s_pos, s_ref, s_minmask, s_wpre, s_ent, s_hi, s_fbmask, s_invalid, s_invpre, out);
-            __syncwarp();
-
-            // colliding minimizers: every k-mer of the run goes through fallback_kmer_order (rare)
-            if (!simple) {
-                const uint32_t fb_any = lane < kMaskWords ? s_fbmask[lane] : 0u;
-                if (__any_sync(0xFFFFFFFFu, fb_any != 0))
-                    fallback_kmers<K, M, kTile>(f, s_packed, s_fbmask, s_invalid, s_invpre, lane, out);
-            }
         }
+
+        // ------------------------------------------------------------ E: emit -----------------------
+        uint64_t* out = b.codes + cur.out;
+        if (!__any_sync(0xFFFFFFFFu, special)) {
+            if (!tile_has_invalid) emit_plain<kTile>(lane, s_pos, s_ent, out);
+            else emit_masked<kTile>(lane, s_pos, s_ent, s_invalid, s_invpre, out);
+        } else {
+            emit_general<kTile>(lane, s_pos, s_ent, s_fbmask, s_invalid, s_invpre, out);
+            slow_kmers<K, M, kTile>(f, s_packed, s_pos, s_ent, s_fbmask, s_invalid, s_invpre, lane, out);
+        }
+        __syncwarp();
     }  // tiles of this warp
 }
 
@@ -900,19 +920,29 @@ __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, u
     recs[t] = r;
 }
 
+// CTAs of one instantiation that fit a device at once, looked up per device (a process may drive
+// several GPUs from several host threads)
 template <int K, int M, bool kScan>
-void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaStream_t stream) {
-    static bool configured = false;  // per instantiation; the attribute is per device function
-    static int resident = 0;         // CTAs that fit the device at once
-    if (!configured) {
+int resident_ctas() {
+    static std::mutex mu;
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cached[dev]) {
         cudaFuncSetAttribute(k_query_tiled<K, M, kScan>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_query_tiled<K, M, kScan>, kThreads, kSmemBytes);
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-        configured = true;
+        cached[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
+    return cached[dev];
+}
+
+template <int K, int M, bool kScan>
+void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaStream_t stream) {
+    const int resident = resident_ctas<K, M, kScan>();
     // persistent grid: every warp walks tiles (global warp id) + i * (number of warps)
     const uint32_t ctas_needed = (a.n_tiles + kWarps - 1) / kWarps;
     const uint32_t grid = ctas_needed < uint32_t(resident) ? ctas_needed : uint32_t(resident);

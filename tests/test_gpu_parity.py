@@ -283,3 +283,81 @@ def test_scan_classify_fused_matches_reference_golden(golden):
     assert nk == int(golden.n_kmers) and mm == int(golden.mm_count)
     assert np.array_equal(trip, golden.triplets)
     assert np.array_equal(ids, golden.coll_ids)
+
+
+# ---- branches the bundled-size fixtures do not reach on their own -------------------------------
+
+def test_forced_wide_bucket_table_matches_golden(golden, monkeypatch):
+    """The 64-bit bucket table (taken on its own only by indexes with a base >= 2^30, i.e. BASELINE
+    config 3) forced on every golden through the loader's test hook."""
+    monkeypatch.setenv("LPHB_FORCE_WIDE_BUCKETS", "1")
+    f = api.Mphf.load(golden.lph, golden.bits)
+    monkeypatch.delenv("LPHB_FORCE_WIDE_BUCKETS")
+    try:
+        narrow = api.Mphf.load(golden.lph, golden.bits)
+        assert f.info.device_bytes > narrow.info.device_bytes  # 8 instead of 4 bytes per table slot
+        narrow.close()
+        codes, code_off = f.query_batch(golden.q_bases, golden.q_offsets)
+        assert np.array_equal(code_off, golden.q_code_offsets)
+        assert np.array_equal(codes, golden.q_codes)
+        codes, _ = f.query_batch(golden.index_bases, golden.index_offsets)
+        n = f.get_kmer_count()
+        assert len(codes) == n and np.array_equal(np.sort(codes), np.arange(n, dtype=np.uint64))
+    finally:
+        f.close()
+
+
+@pytest.mark.parametrize("name", ["k31_m20_u64", "k63_m24_u128", "k21_m11_u64", "k25_m13_u64"])
+@pytest.mark.parametrize("wide", [False, True])
+def test_non_member_flood_hits_every_table_slot(name, wide, monkeypatch):
+    """Random (non-member) sequence probes arbitrary PTHash slots, among them the few whose code
+    underflows 64 bits for a non-member offset (hval = base - p with base < p, taken mod 2^64 by
+    the reference: SURVEY.md E1 vii) - the entries the 32-bit fast emit must hand to the exact path."""
+    g = load_golden(name)
+    if wide:
+        monkeypatch.setenv("LPHB_FORCE_WIDE_BUCKETS", "1")
+    f = api.Mphf.load(g.lph, g.bits)
+    try:
+        o = oracle.OracleMphf(g.lph, g.bits)
+        rng = np.random.Generator(np.random.PCG64(0xF100D + g.k))
+        n_bases = int(min(6_000_000, max(1_000_000, 12 * f.get_minimizer_L0() * (g.k - g.m + 2) // 2)))
+        bases = synth.random_bases(n_bases, rng)
+        cuts = np.sort(rng.choice(np.arange(1, n_bases), size=40, replace=False))
+        offsets = np.concatenate([[0], cuts, [n_bases]]).astype(np.uint64)
+        want, want_off = o.query_batch(bases, offsets)
+        got, got_off = f.query_batch(bases, offsets)
+        assert np.array_equal(got_off, want_off)
+        assert np.array_equal(got, want)
+    finally:
+        f.close()
+
+
+def test_small_probe_chunks_variant():
+    """Phase D probes the minimizers of a tile in chunks of 256; the `listcap32` build of the library
+    (csrc/Makefile: testvariants) cuts them at 32 so that every tile takes several chunks, and sends
+    every bucket with a base below 60000 through the exact 64-bit path that otherwise only codes
+    outside 32 bits take."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = os.path.join(os.path.dirname(here), "lphash_b200", "liblphash_b200_listcap32.so")
+    if not os.path.exists(lib):
+        pytest.skip("variant library not built (make -C lphash_b200/csrc testvariants)")
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(here)!r}); sys.path.insert(0, {here!r})\n"
+        "from conftest import load_golden\n"
+        "from lphash_b200 import api\n"
+        "for name in ['k31_m20_u64', 'k15_m7_u64', 'k63_m24_u128']:\n"
+        "    g = load_golden(name)\n"
+        "    f = api.Mphf.load(g.lph, g.bits)\n"
+        "    codes, off = f.query_batch(g.q_bases, g.q_offsets)\n"
+        "    assert np.array_equal(off, g.q_code_offsets) and np.array_equal(codes, g.q_codes), name\n"
+        "    codes, _ = f.query_batch(g.index_bases, g.index_offsets)\n"
+        "    assert np.array_equal(np.sort(codes), np.arange(f.get_kmer_count(), dtype=np.uint64)), name\n"
+        "    f.close()\n"
+        "print('ok')\n")
+    env = dict(os.environ, LPHASH_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
