@@ -99,6 +99,7 @@ struct Entry {
     uint32_t lo;
     int32_t nsq;                               // -1: LEFT/MAXIMAL, +1: RIGHT/NONE, 0: see above
 };
+constexpr int kSpecCap = 60;                   // irregular entries per tile the fix-up pass takes (more: whole tile the slow way)
 constexpr int kPackedSlots = 68;               // packed words per tile: 64 + zero read-ahead of mmer_at / win16
 constexpr int kRawBytes = 1024;                // ASCII bytes of one tile incl. overlap (64 words), one TMA copy
 // per-warp shared memory (bytes)
@@ -106,7 +107,7 @@ constexpr int kOffEnt = 0;                               // Entry[kSlots], by mi
 constexpr int kOffPos = kOffEnt + kSlots * 8;            // u8[kSlots]  per k-mer start: thread-local minimizer position
 constexpr int kOffList = kOffPos + kSlots;               // u16[kListCap] minimizer positions of the chunk
 constexpr int kOffMin = kOffList + kListCap * 2;         // u32[32] minimizer-position mask
-constexpr int kOffFb = kOffMin + 128;                    // u32[32] k-mers that need the slow path
+constexpr int kOffFb = kOffMin + 128;                    // u32 count + u16[kSpecCap]: irregular entries for the fix-up pass
 constexpr int kOffInv = kOffFb + 128;                    // u32[32] invalid starts
 constexpr int kOffInvPre = kOffInv + 128;                // u16[32] invalid starts before mask word
 constexpr int kOffPacked = kOffInvPre + 64;              // u32[kPackedSlots]
@@ -390,29 +391,6 @@ __device__ __forceinline__ void emit_masked(int lane, const uint8_t* s_pos, cons
     }
 }
 
-// General form, for a tile with an entry the fast forms cannot use (nsq == 0): regular k-mers as
-// above, the others are flagged in s_fbmask and finished by slow_kmers.  Out of line.
-template <int kTile>
-static __device__ __noinline__ void emit_general(int lane, const uint8_t* s_pos, const Entry* s_ent,
-                                                 uint32_t* s_fbmask, const uint32_t* s_invalid,
-                                                 const uint16_t* s_invpre, uint64_t* out) {
-    const int lane16 = lane & 16;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint64_t* out_l = out + lane;
-#pragma unroll 2
-    for (int r = 0; r < kTile / 32; ++r) {
-        const int q = lane + r * 32;
-        const uint32_t mw = s_invalid[r];  // uniform in the warp
-        const bool ok = !((mw >> lane) & 1u);
-        const Entry e = s_ent[ok ? int(s_pos[q]) + lane16 + r * 32 : 0];
-        const uint32_t slow = __ballot_sync(0xFFFFFFFFu, ok && e.nsq == 0);
-        if (lane == 0) s_fbmask[r] = slow;
-        if (ok && e.nsq != 0)
-            __stcs(out_l + (r * 32 - int(s_invpre[r]) - __popc(mw & lt)), uint64_t(e.lo + uint32_t(e.nsq * q)));
-    }
-    __syncwarp();
-}
-
 // k-mer starts of a tile that produce no code (contig seams, short contigs, positions outside
 // [first, end)) -> s_invalid.  Only for tiles that one contig does not cover: out of line, away from
 // the hot loop's instruction-cache footprint.
@@ -461,36 +439,62 @@ static __device__ __noinline__ void mark_invalid(DevBatch const& b, uint32_t* s_
     __syncwarp();
 }
 
-// The k-mers the fast emit left out (s_fbmask), one lane per k-mer:
-//   * colliding minimizer (entry lo == 0): code = collision base + fallback_kmer_order(k-mer)
-//     (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134);
-//   * code outside 32 bits (entry lo == 1): the probe is redone and evaluated in 64 bits, mod 2^64
-//     like the reference (partitioned_mphf.cpp:337; non-members may underflow, SURVEY.md E1 vii).
-// Lane l takes bit l of every mask word, so the consecutive k-mers of a run spread over the lanes
-// and their (dependent, uncached) gathers overlap.  Rare: out of line.
+// Exact code of the k-mer starting at tile-local g whose minimizer sits at tile-local mp, without the
+// 32-bit shortcuts: the probe in full, hval mod 2^64 like the reference (partitioned_mphf.cpp:337;
+// non-members may underflow, SURVEY.md E1 vii), colliding minimizers through fallback_kmer_order
+// (partitioned_mphf.cpp:308-313, partitioned_mphf.hpp:132-134).  Used where the fast emit cannot be.
+template <int K, int M>
+static __device__ __noinline__ uint64_t exact_code(DevImage const& f, const uint32_t* s_packed, int g, int mp) {
+    const Probe pr = probe_minimizer(f, mmer_at<M>(s_packed, mp));
+    if (pr.slope != 0) return probe_hval(pr, uint32_t(mp - g));
+    uint64_t klo, khi;
+    kmer_at<K, Cfg<K, M>::NW>(s_packed, g, klo, khi);
+    return f.collision_base + fallback_order(f, klo, khi);
+}
+
+// where the code of valid start q goes (dense order: starts without a code are skipped)
+__device__ __forceinline__ int out_index(const uint32_t* s_invalid, const uint16_t* s_invpre, int q) {
+    const uint32_t mw = s_invalid[q >> 5];
+    return q - int(s_invpre[q >> 5]) - __popc(mw & ((1u << (q & 31)) - 1u));
+}
+
+// Fix-up pass after the fast emit: the k-mers of the (few) minimizers whose entry is not regular
+// (s_spec: their positions).  A minimizer at position bp can only serve the starts bp-W+1 .. bp: one
+// lane per candidate start, two minimizers per pass when the window fits half a warp.  Out of line.
 template <int K, int M, int kTile>
-static __device__ __noinline__ void slow_kmers(DevImage const& f, const uint32_t* s_packed, const uint8_t* s_pos,
-                                               const Entry* s_ent, const uint32_t* s_fbmask,
-                                               const uint32_t* s_invalid, const uint16_t* s_invpre, int lane,
-                                               uint64_t* out) {
-    constexpr int NW = Cfg<K, M>::NW, kMaskWords = kTile / 32;
+static __device__ __noinline__ void fix_special(DevImage const& f, const uint32_t* s_packed, const uint8_t* s_pos,
+                                                const uint16_t* s_spec, uint32_t n_spec, const uint32_t* s_invalid,
+                                                const uint16_t* s_invpre, int lane, uint64_t* out) {
+    constexpr int W = K - M + 1;
+    constexpr int G = W <= 16 ? 16 : 32;   // lanes per minimizer
+    constexpr int R = (W + G - 1) / G;     // rounds of G candidate starts
 #pragma unroll 1
-    for (int r = 0; r < kMaskWords; ++r) {
-        const uint32_t fw = s_fbmask[r];  // uniform
-        if (!((fw >> lane) & 1u)) continue;
-        const int g = r * 32 + lane;
-        const int mp = int(s_pos[g]) + (lane & 16) + r * 32;  // tile-local position of g's minimizer
-        uint64_t code;
-        if (s_ent[mp].lo == 0u) {
-            uint64_t klo, khi;
-            kmer_at<K, NW>(s_packed, g, klo, khi);
-            code = f.collision_base + fallback_order(f, klo, khi);
-        } else {
-            const Probe pr = probe_minimizer(f, mmer_at<M>(s_packed, mp));
-            code = probe_hval(pr, uint32_t(mp - g));
+    for (uint32_t s0 = 0; s0 < n_spec; s0 += 32 / G) {
+        const uint32_t s = s0 + uint32_t(lane / G);
+        const int bp = s < n_spec ? int(s_spec[s]) : -1;
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            const int j = (lane % G) + r * G;
+            const int q = bp - j;
+            if (bp < 0 || j >= W || q < 0 || q >= kTile) continue;
+            if ((s_invalid[q >> 5] >> (q & 31)) & 1u) continue;
+            if (int(s_pos[q]) + (q & ~15) != bp) continue;  // q's minimizer is another position
+            out[out_index(s_invalid, s_invpre, q)] = exact_code<K, M>(f, s_packed, q, bp);
         }
-        const uint32_t mw = s_invalid[r];
-        out[g - int(s_invpre[r] + __popc(mw & ((1u << lane) - 1u)))] = code;
+    }
+    __syncwarp();
+}
+
+// A whole tile the slow way, one lane per start and a full probe per k-mer: tiles with more irregular
+// entries than the fix-up pass takes.  Out of line.
+template <int K, int M, int kTile>
+static __device__ __noinline__ void slow_tile(DevImage const& f, const uint32_t* s_packed, const uint8_t* s_pos,
+                                              const uint32_t* s_invalid, const uint16_t* s_invpre, int lane,
+                                              uint64_t* out) {
+#pragma unroll 1
+    for (int q = lane; q < kTile; q += 32) {
+        if ((s_invalid[q >> 5] >> (q & 31)) & 1u) continue;
+        out[out_index(s_invalid, s_invpre, q)] = exact_code<K, M>(f, s_packed, q, int(s_pos[q]) + (q & ~15));
     }
     __syncwarp();
 }
@@ -515,7 +519,8 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
     uint8_t* s_pos = mine + kOffPos;                                  // per k-mer: thread-local minimizer position
     uint16_t* s_list = reinterpret_cast<uint16_t*>(mine + kOffList);  // minimizer positions of the chunk
     uint32_t* s_minmask = reinterpret_cast<uint32_t*>(mine + kOffMin);  // bit p: position p is some k-mer's minimizer
-    uint32_t* s_fbmask = reinterpret_cast<uint32_t*>(mine + kOffFb);    // bit q: k-mer q goes through slow_kmers
+    uint32_t* s_spec32 = reinterpret_cast<uint32_t*>(mine + kOffFb);    // [0]: irregular entries of the tile, then their positions (u16)
+    uint16_t* s_spec = reinterpret_cast<uint16_t*>(s_spec32 + 1);
     uint32_t* s_invalid = reinterpret_cast<uint32_t*>(mine + kOffInv);  // bit q: k-mer start q produces no code
     uint16_t* s_invpre = reinterpret_cast<uint16_t*>(mine + kOffInvPre);  // invalid starts before mask word
     uint32_t* s_packed = reinterpret_cast<uint32_t*>(mine + kOffPacked);  // 2-bit bases of the tile
@@ -781,7 +786,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         // ------------------------------------------------------------ D: probe ---------------------
         // one lane per distinct minimizer position, in chunks of kListCap (one chunk unless the window
         // is tiny or the hashes of the tile descend); the entries go to s_ent[position]
-        bool special = false;
+        if (lane == 0) s_spec32[0] = 0;
         const DevPhf& P = f.minimizer_order;
         const uint64_t keep = l2_keep_policy();
         const bool wide = f.buckets.wide != 0;
@@ -868,13 +873,11 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
                         care |= base < uint32_t(LPHB_TEST_CARE_BELOW);
 #endif
                         Entry e;
-                        if (colliding | care) {
-                            e.lo = colliding ? 0u : 1u;
-                            e.nsq = 0;
-                            special = true;
-                        } else {
-                            e.lo = base - uint32_t(nsq * bp[u]);
-                            e.nsq = nsq;
+                        e.lo = base - uint32_t(nsq * bp[u]);
+                        e.nsq = nsq;
+                        if (colliding | care) {  // rare: the fast emit's code for these k-mers is overwritten afterwards
+                            const uint32_t n = atomicAdd(s_spec32, 1u);
+                            if (n < uint32_t(kSpecCap)) s_spec[n] = uint16_t(bp[u]);
                         }
                         s_ent[bp[u]] = e;
                     }
@@ -885,12 +888,15 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
 
         // ------------------------------------------------------------ E: emit -----------------------
         uint64_t* out = b.codes + cur.out;
-        if (!__any_sync(0xFFFFFFFFu, special)) {
-            if (!tile_has_invalid) emit_plain<kTile>(lane, s_pos, s_ent, out);
-            else emit_masked<kTile>(lane, s_pos, s_ent, s_invalid, s_invpre, out);
-        } else {
-            emit_general<kTile>(lane, s_pos, s_ent, s_fbmask, s_invalid, s_invpre, out);
-            slow_kmers<K, M, kTile>(f, s_packed, s_pos, s_ent, s_fbmask, s_invalid, s_invpre, lane, out);
+        if (!tile_has_invalid) emit_plain<kTile>(lane, s_pos, s_ent, out);
+        else emit_masked<kTile>(lane, s_pos, s_ent, s_invalid, s_invpre, out);
+        // irregular entries (colliding minimizers, codes outside 32 bits): their k-mers again, exactly
+        __syncwarp();
+        const uint32_t n_spec = s_spec32[0];
+        if (n_spec) {
+            __syncwarp();
+            if (n_spec <= uint32_t(kSpecCap)) fix_special<K, M, kTile>(f, s_packed, s_pos, s_spec, n_spec, s_invalid, s_invpre, lane, out);
+            else slow_tile<K, M, kTile>(f, s_packed, s_pos, s_invalid, s_invpre, lane, out);
         }
         __syncwarp();
     }  // tiles of this warp
