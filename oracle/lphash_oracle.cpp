@@ -9,12 +9,14 @@
 // time.  Every function cites the reference lines it restates ("ref:" = /root/reference/,
 // "pthash/" = external/pthash/).
 //
-// PARITY IS PINNED: tests/test_oracle_vs_reference.py checks this file against the unmodified
-// reference compiled into oracle/_ref/libref{64,128}.so (oracle/build_ref.sh) on the bundled
-// data (all four super-k-mer types, collisions, the non-ACGT streaming quirk, both kmer_t
-// flavours, k=31/47/63), and tests/test_oracle_golden.py checks it against the committed golden
-// fixtures in tests/golden/ (generated from the reference by tools/make_golden.py) so that the
-// pin also holds on the GPU box where /root/reference does not exist.
+// PARITY IS PINNED: tests/test_oracle_vs_reference.py checks this file against what the unmodified
+// reference (compiled into oracle/_ref/ by oracle/build_ref.sh) returned on its own bundled data
+// (BASELINE config 1: se.ust.k31 index k=31 m=16 128-bit, the three bundled query files incl. the
+// non-ACGT streaming quirk of ecoli1.fasta and the FASTQ, and the from_string stream; inputs and
+// expected outputs committed under tests/golden/config1/ by tools/make_config1.py - the folds are
+// those of SURVEY.md section 8c), and tests/test_oracle_golden.py checks it against the committed
+// golden fixtures in tests/golden/ (8 (k, m, kmer_t) combinations, generated from the reference by
+// tools/make_golden.py), so that the pin also holds on the GPU box where /root/reference does not exist.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
