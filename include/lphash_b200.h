@@ -83,16 +83,47 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets,
                       uint64_t n_contigs, uint64_t* codes, uint64_t codes_capacity,
                       uint64_t* code_offsets, uint64_t* n_codes);
 
+/* Same call with the codes returned in RUN-LENGTH form: consecutive k-mers of a super-k-mer get
+ * consecutive codes (include/partitioned_mphf.hpp:131-145: local_rank +-1 per k-mer), so the vector
+ * the reference returns is a sequence of arithmetic runs.  `runs` receives packed 12-byte records
+ * {uint64_t first; int32_t n} (little-endian; n > 0: first, first+1, ... n codes; n < 0: first,
+ * first-1, ... |n| codes), in stream order and never across a contig start: about 2 bytes per k-mer
+ * over PCIe instead of 8.  lphb_expand_runs rebuilds the identical uint64_t vector on the host.
+ * Works for any input (non-members, colliding minimizers, non-ACGT contigs: their runs are just
+ * shorter).  A batch must hold fewer than 2^31 k-mers.  n_runs is also set when returning
+ * LPHB_E_CAPACITY (which is also what runs == NULL returns after reporting n_runs / n_codes /
+ * code_offsets).                                                                                  */
+int lphb_query_stream_runs(lphb_mphf* f, const char* bases, const uint64_t* offsets,
+                           uint64_t n_contigs, void* runs, uint64_t runs_capacity, uint64_t* n_runs,
+                           uint64_t* code_offsets, uint64_t* n_codes);
+
+/* Host-only decoding of run records into the codes of lphb_query_stream (same order, same values);
+ * `threads` host threads share the work (<= 1: the calling thread).  n_codes is also set when
+ * returning LPHB_E_CAPACITY.                                                                       */
+int lphb_expand_runs(const void* runs, uint64_t n_runs, uint64_t* codes, uint64_t codes_capacity,
+                     uint64_t* n_codes, int threads);
+
 /* Device-resident variant: d_* are device pointers on the handle's GPU, `stream` is a
  * cudaStream_t (NULL = default stream).  Asynchronous.  h_offsets is the host copy of the same
  * offsets (used only for sizes).  Evaluates the stateless definition (one code per window of k
- * valid bases); d_status[0] = number of codes laid out (sum of max(0, L-k+1)), d_status[1] =
- * number of contigs containing a non-ACGT byte (their code ranges then hold only the valid
- * k-mers' codes; lphb_query_stream runs the exact fix-up for those, this call does not).       */
+ * ACGT bases); d_status[0] = number of codes laid out (sum of max(0, L-k+1)),
+ * d_status[1] = number of contigs containing a non-ACGT byte.  For such a contig the code slot of
+ * every k-mer window that contains a non-ACGT byte is UNSPECIFIED (the slots of its other k-mers hold
+ * their codes); lphb_mphf_dirty_flags names those contigs, and lphb_query_stream applies the
+ * reference's exact streaming behaviour to them - this call does not.
+ * Ordering: a handle owns one device workspace, so consecutive calls on one handle are ordered on
+ * the device (each call makes its stream wait for the previous call's kernels), on whatever
+ * streams they are issued; they never overlap each other.  Overlap comes from several handles or
+ * from the copies of the caller's other streams.                                                  */
 int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* d_offsets,
                              const uint64_t* h_offsets, uint64_t n_contigs, uint64_t* d_codes,
                              uint64_t codes_capacity, uint64_t* d_code_offsets,
                              uint64_t* d_status, void* stream);
+
+/* Per-contig flags of the last query call on the handle: *d_flags = DEVICE pointer to *n_contigs
+ * bytes, nonzero where the contig contains a non-ACGT byte; valid (in stream order) until the next
+ * query call on the handle.                                                                        */
+int lphb_mphf_dirty_flags(const lphb_mphf* f, const uint8_t** d_flags, uint64_t* n_contigs);
 
 /* ---- build-p Part 1: minimizer / super-k-mer scan -------------------------------------------
  * Replaces the loop over minimizer::from_string (include/minimizer.hpp:11-170; caller

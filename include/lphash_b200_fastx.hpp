@@ -61,7 +61,9 @@ inline uint64_t parse(const char* data, size_t n, Batch& out) {
             }
             const char* e = line_end(p);
             size_t len = size_t(e - p);
-            if (len && p[len - 1] == '\r') --len;  // kseq drops the '\r' of "\r\n"
+            // kseq drops the '\r' of "\r\n", but only once the accumulated sequence is longer than one
+            // character (ks_getuntil2: `str->l > 1`): a lone "\r" first line stays a base
+            if (len && p[len - 1] == '\r' && (out.bases.size() - seq_begin) + len > 1) --len;
             out.bases.insert(out.bases.end(), p, p + len);
             p = e < end ? e + 1 : end;
         }
@@ -77,7 +79,7 @@ inline uint64_t parse(const char* data, size_t n, Batch& out) {
             while (ok && p < end) {
                 const char* e = line_end(p);
                 size_t len = size_t(e - p);
-                if (len && p[len - 1] == '\r') --len;
+                if (len && p[len - 1] == '\r' && qual + len > 1) --len;  // same rule on the quality string
                 qual += len;
                 p = e < end ? e + 1 : end;
                 if (qual >= seq_len) break;

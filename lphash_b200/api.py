@@ -50,7 +50,8 @@ class Stats(C.Structure):
 EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_load_file",
            "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
-           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify"]
+           "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify",
+           "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags"]
 
 _lib = None
 
@@ -75,6 +76,9 @@ def lib() -> C.CDLL:
     L.lphb_mphf_stats.argtypes = [p, C.POINTER(Stats)]
     L.lphb_query_stream.argtypes = [p, p, p, u64, p, u64, p, C.POINTER(u64)]
     L.lphb_query_stream_device.argtypes = [p, p, p, p, u64, p, u64, p, p, p]
+    L.lphb_query_stream_runs.argtypes = [p, p, p, u64, p, u64, C.POINTER(u64), p, C.POINTER(u64)]
+    L.lphb_expand_runs.argtypes = [p, u64, p, u64, C.POINTER(u64), i32]
+    L.lphb_mphf_dirty_flags.argtypes = [p, C.POINTER(p), C.POINTER(u64)]
     L.lphb_scan_superkmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
                                        u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_colliding_kmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
@@ -189,6 +193,20 @@ class Mphf:
                                        codes.ctypes.data, cap, code_off.ctypes.data, C.byref(total)))
         return codes[: total.value], code_off
 
+    def query_batch_runs(self, bases, offsets, out: np.ndarray | None = None):
+        """lphb_query_stream_runs: the codes of a batch in run-length form (RUN_DTYPE records, about
+        2 bytes per k-mer over PCIe instead of 8).  Returns (runs, code_offsets, n_codes)."""
+        bases, offsets = _as_batch(bases, offsets)
+        n = len(offsets) - 1
+        lens = np.diff(offsets).astype(np.int64)
+        cap = int(np.maximum(lens - self.m + 1, 0).sum()) if out is None else len(out)
+        runs = np.empty(max(cap, 1), dtype=RUN_DTYPE) if out is None else out
+        code_off = np.empty(n + 1, dtype=np.uint64)
+        n_runs, total = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().lphb_query_stream_runs(self._h, bases.ctypes.data, offsets.ctypes.data, n, runs.ctypes.data,
+                                            cap, C.byref(n_runs), code_off.ctypes.data, C.byref(total)))
+        return runs[: n_runs.value], code_off, total.value
+
     def query_device(self, d_bases: int, d_offsets: int, h_offsets: np.ndarray, d_codes: int,
                      capacity: int, d_code_offsets: int, d_status: int, stream: int = 0) -> None:
         """Device-resident asynchronous variant; arguments are raw device pointers (ints), e.g.
@@ -197,6 +215,19 @@ class Mphf:
         _check(lib().lphb_query_stream_device(self._h, d_bases, d_offsets, h_offsets.ctypes.data,
                                               len(h_offsets) - 1, d_codes, capacity, d_code_offsets,
                                               d_status, stream))
+
+
+RUN_DTYPE = np.dtype([("first", "<u8"), ("n", "<i4")])  # 12 bytes packed: lphb_query_stream_runs records
+
+
+def expand_runs(runs, threads: int = 1) -> np.ndarray:
+    """lphb_expand_runs: run records -> the uint64 codes lphb_query_stream returns (host only)."""
+    runs = np.ascontiguousarray(runs, dtype=RUN_DTYPE)
+    total = int(np.abs(runs["n"].astype(np.int64)).sum())
+    codes = np.empty(max(total, 1), dtype=np.uint64)
+    n = C.c_uint64(0)
+    _check(lib().lphb_expand_runs(runs.ctypes.data, len(runs), codes.ctypes.data, total, C.byref(n), threads))
+    return codes[: n.value]
 
 
 # ---- build-side scan (module-level like the reference's free functions in namespace minimizer) --

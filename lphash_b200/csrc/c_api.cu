@@ -8,10 +8,12 @@
 #include <cstring>
 #include <fstream>
 #include <new>
+#include <algorithm>
 #include <chrono>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lphash_b200.h"
@@ -64,12 +66,29 @@ struct DevBuf {
 
 struct Workspace {
     DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
+    DevBuf r_start, r_head, r_rank, r_head_at, r_tmp, r_runs, r_count;  // run-length form of the codes (lphb_query_stream_runs)
+    unsigned long long* h_counts = nullptr;  // pinned: runs per chunk
+    uint64_t h_counts_cap = 0;
+    std::vector<cudaEvent_t> ev_cnt;         // per chunk: its run count has reached h_counts
     unsigned long long* h_status = nullptr;  // pinned, 4 words
     cudaStream_t stream = nullptr;
     // chunk pipeline of lphb_query_stream: two extra streams so that the H2D copy of chunk j+1,
     // the kernels of chunk j and the D2H copy of chunk j-1 overlap (PCIe is full duplex)
     cudaStream_t cs[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready = nullptr, ev_done[2] = {nullptr, nullptr};
+    // The handle has ONE device workspace (dirty flags, tile records, scan scratch).  Calls may arrive
+    // on different streams (lphb_query_stream_device takes the caller's): every call first makes its
+    // stream wait for the previous call's last kernel, so that two calls never share the workspace
+    // in time; their device work is ordered, whatever the streams.
+    cudaEvent_t ev_last = nullptr;
+    bool have_last = false;
+    void order_after_previous(cudaStream_t st) {
+        if (have_last) CK(cudaStreamWaitEvent(st, ev_last, 0));
+    }
+    void mark_last(cudaStream_t st) {
+        CK(cudaEventRecord(ev_last, st));
+        have_last = true;
+    }
     void ensure_pipeline() {
         if (cs[0]) return;
         for (int i = 0; i < 2; ++i) {
@@ -85,6 +104,7 @@ struct Workspace {
     void init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaMallocHost(reinterpret_cast<void**>(&h_status), 4 * sizeof(unsigned long long)));
+        CK(cudaEventCreateWithFlags(&ev_last, cudaEventDisableTiming));
         for (int i = 0; i < kEvRing; ++i) {
             CK(cudaEventCreate(&ev0[i]));
             CK(cudaEventCreate(&ev1[i]));
@@ -93,8 +113,10 @@ struct Workspace {
     }
     void destroy() {
         for (DevBuf* b : {&bases, &offsets, &code_off, &codes, &dirty, &status, &tmp, &aux0, &aux1,
-                          &aux2, &aux3, &codes2, &tile})
+                          &aux2, &aux3, &codes2, &tile, &r_start, &r_head, &r_rank, &r_head_at, &r_tmp, &r_runs, &r_count})
             b->release();
+        if (h_counts) cudaFreeHost(h_counts);
+        for (cudaEvent_t e : ev_cnt) cudaEventDestroy(e);
         if (h_status) cudaFreeHost(h_status);
         for (int i = 0; i < kEvRing; ++i) {
             if (ev0[i]) cudaEventDestroy(ev0[i]);
@@ -106,6 +128,7 @@ struct Workspace {
             if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         }
         if (ev_ready) cudaEventDestroy(ev_ready);
+        if (ev_last) cudaEventDestroy(ev_last);
     }
 };
 
@@ -137,6 +160,7 @@ struct lphb_mphf {
     std::vector<cudaStream_t> l2_streams;  // streams the window is attached to
     lphb_info info{};
     lphb_stats stats{};
+    uint64_t last_dirty_n = 0;  // contigs of the last query call (length of the dirty-flag array)
     Workspace ws;
 };
 
@@ -291,13 +315,21 @@ int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int
 
 int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out) {
     if (!path) return fail(LPHB_E_ARG, "path is null");
-    std::ifstream in(path, std::ios::binary | std::ios::ate);
-    if (!in.good()) return fail(LPHB_E_IO, std::string("cannot open ") + path);
-    std::streamsize n = in.tellg();
-    in.seekg(0);
-    std::vector<uint8_t> buf(static_cast<size_t>(n));
-    if (n && !in.read(reinterpret_cast<char*>(buf.data()), n)) return fail(LPHB_E_IO, "short read");
-    return load_image(buf.data(), uint64_t(n), kmer_bits, device, out);
+    if (!out) return fail(LPHB_E_ARG, "out is null");
+    *out = nullptr;
+    std::vector<uint8_t> buf;
+    int rc = guarded([&]() -> int {  // allocation failures must not cross the C boundary either
+        std::ifstream in(path, std::ios::binary | std::ios::ate);
+        if (!in.good()) return fail(LPHB_E_IO, std::string("cannot open ") + path);
+        const std::streamoff n = in.tellg();
+        if (n < 0) return fail(LPHB_E_IO, std::string("cannot size ") + path);
+        in.seekg(0);
+        buf.resize(static_cast<size_t>(n));
+        if (n && !in.read(reinterpret_cast<char*>(buf.data()), n)) return fail(LPHB_E_IO, "short read");
+        return LPHB_OK;
+    });
+    if (rc != LPHB_OK) return rc;
+    return load_image(buf.data(), uint64_t(buf.size()), kmer_bits, device, out);
 }
 
 int lphb_mphf_free(lphb_mphf* f) {
@@ -305,6 +337,16 @@ int lphb_mphf_free(lphb_mphf* f) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(f->device);
+    cudaDeviceSynchronize();  // no call of this handle may still be in flight
+    if (f->l2_window_bytes) {
+        // the access-policy window points into the arena that is about to be freed
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        for (cudaStream_t t : f->l2_streams)
+            if (t != f->ws.stream && t != f->ws.cs[0] && t != f->ws.cs[1])
+                if (cudaStreamSetAttribute(t, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        cudaCtxResetPersistingL2Cache();
+    }
     f->ws.destroy();
     if (f->d_arena) cudaFree(f->d_arena);
     if (prev >= 0) cudaSetDevice(prev);
@@ -346,6 +388,13 @@ int lphb_mphf_stats(const lphb_mphf* cf, lphb_stats* stats) {
     return LPHB_OK;
 }
 
+int lphb_mphf_dirty_flags(const lphb_mphf* f, const uint8_t** d_flags, uint64_t* n_contigs) {
+    if (!f || !d_flags || !n_contigs) return fail(LPHB_E_ARG, "null argument");
+    *d_flags = f->ws.dirty.as<uint8_t>();
+    *n_contigs = f->last_dirty_n;
+    return LPHB_OK;
+}
+
 int lphb_host_alloc(void** ptr, uint64_t nbytes) {
     if (!ptr) return fail(LPHB_E_ARG, "ptr is null");
     cudaError_t e = cudaMallocHost(ptr, nbytes ? nbytes : 1);
@@ -381,8 +430,12 @@ int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* 
         if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
         if (total && (!d_bases || !d_codes)) return fail(LPHB_E_ARG, "null data pointer");
         Workspace& ws = f->ws;
+        // (growing a workspace buffer frees the old one: cudaFree waits for the device, so a previous
+        // call still running never loses its buffer)
         ws.tmp.reserve(code_offsets_tmp_bytes(n_contigs));
         ws.dirty.reserve(n_contigs + 8);
+        ws.tile.reserve(query_tiled_ws_bytes(h_offsets[n_contigs] - h_offsets[0]));
+        ws.order_after_previous(s);
         CK(cudaMemsetAsync(ws.dirty.p, 0, n_contigs + 8, s));
         auto* st = reinterpret_cast<unsigned long long*>(d_status);
         launch_code_offsets(d_offsets, n_contigs, k, d_code_offsets, st, ws.tmp.p, ws.tmp.cap, s);
@@ -397,24 +450,47 @@ int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* 
         b.codes = d_codes;
         b.dirty = ws.dirty.as<uint8_t>();
         b.status = st;
-        ws.tile.reserve(query_tiled_ws_bytes(b.end_base - b.first_base));
         b.tile_ws = ws.tile.p;
         b.tile_ws_bytes = ws.tile.cap;
         if (n_contigs) run_kernels(f, b, s);
+        ws.mark_last(s);
+        f->last_dirty_n = n_contigs;
         CK(cudaGetLastError());
         return LPHB_OK;
     });
 }
 
-int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
-                      uint64_t* codes, uint64_t codes_capacity, uint64_t* code_offsets,
-                      uint64_t* n_codes) {
-    if (!f || !offsets || !code_offsets || !n_codes) return fail(LPHB_E_ARG, "null argument");
+}  // extern "C"
+
+namespace {
+
+// What the caller wants back: the codes themselves (8 B per k-mer) or their run-length form (12-byte
+// records, about 2 B per k-mer: runs_kernels.cu).
+struct RunSink {
+    void* runs = nullptr;        // null: codes mode
+    uint64_t capacity = 0;
+    uint64_t* n_runs = nullptr;
+};
+
+// scratch of the run-length pass for a stream of n codes
+void reserve_runs(Workspace& ws, uint64_t n) {
+    ws.r_start.reserve(n + 8);
+    ws.r_head.reserve(n + 8);
+    ws.r_rank.reserve((n + 2) * 4);
+    ws.r_head_at.reserve((n + 2) * 4);
+    ws.r_tmp.reserve(2 * ((runs_tmp_bytes(n) + 255) / 256 * 256));  // one half per scratch set
+}
+
+int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                      uint64_t* codes, uint64_t codes_capacity, uint64_t* code_offsets, uint64_t* n_codes,
+                      RunSink sink) {
+    const bool want_runs = sink.runs != nullptr || sink.n_runs != nullptr;
     return guarded([&]() -> int {
         DeviceGuard g(f->device);
         Workspace& ws = f->ws;
         cudaStream_t s = ws.stream;
         f->stats = lphb_stats{};
+        if (want_runs) *sink.n_runs = 0;
         const uint32_t k = f->img.k, m = f->img.m;
         // layout for clean input: L-k+1 codes per contig (partitioned_mphf.hpp:79-80)
         uint64_t total = 0;
@@ -429,15 +505,18 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         if (n_contigs == 0) return LPHB_OK;
         const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
         if (span && !bases) return fail(LPHB_E_ARG, "bases is null");
+        if (want_runs && total >= (1ull << 31)) return fail(LPHB_E_ARG, "batch holds >= 2^31 k-mers: split it");
         ws.bases.reserve(span + 64);
         ws.offsets.reserve((n_contigs + 1) * 8);
         ws.code_off.reserve((n_contigs + 1) * 8);
         ws.codes.reserve(total * 8 + 64);
         ws.dirty.reserve(n_contigs + 8);
+        ws.order_after_previous(s);  // a device-resident call may still be running on the caller's stream
         CK(cudaMemcpyAsync(ws.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ws.code_off.p, code_offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ws.dirty.p, 0, n_contigs + 8, s));
         CK(cudaMemsetAsync(ws.status.p, 0, 4 * sizeof(unsigned long long), s));
+        f->last_dirty_n = n_contigs;
         f->stats.h2d_bytes = span + 2 * (n_contigs + 1) * 8;
         DevBatch b{};
         b.bases = ws.bases.as<char>() - first;  // kernels index bases[offsets[c] + ...]
@@ -450,8 +529,8 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         b.dirty = ws.dirty.as<uint8_t>();
         b.status = ws.status.as<unsigned long long>();
         // Large batches are cut (on contig boundaries) into chunks that flow through two streams:
-        // H2D of chunk j+1, the kernels of chunk j and the D2H of chunk j-1's codes overlap.  The
-        // codes are copied out optimistically in the clean layout; if some contig turns out to
+        // H2D of chunk j+1, the kernels of chunk j and the D2H of chunk j-1's results overlap.  The
+        // results are copied out optimistically in the clean layout; if some contig turns out to
         // contain a non-ACGT byte the quirk path below rewrites the host buffer.
         std::vector<uint64_t> cuts{0};
         {
@@ -460,7 +539,56 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
                 if (offsets[c + 1] - offsets[cuts.back()] >= chunk && c + 1 < n_contigs) cuts.push_back(c + 1);
             cuts.push_back(n_contigs);
         }
-        const bool pipelined = cuts.size() > 2 && total <= codes_capacity && codes;
+        const uint64_t n_chunks = cuts.size() - 1;
+        const bool pipelined = n_chunks > 1 && (want_runs ? sink.runs != nullptr : (total <= codes_capacity && codes));
+        uint64_t runs_done = 0;       // run records already placed in the caller's buffer
+        bool runs_overflow = false;
+        if (want_runs) {
+            uint64_t max_chunk = 0;
+            for (uint64_t j = 0; j < n_chunks; ++j)
+                max_chunk = std::max<uint64_t>(max_chunk, code_offsets[cuts[j + 1]] - code_offsets[cuts[j]]);
+            // chunks alternate between two scratch sets (their passes overlap across the two streams)
+            const uint64_t per = (pipelined ? max_chunk : total) + 16;
+            reserve_runs(ws, pipelined ? 2 * per : per);
+            ws.r_runs.reserve(total * 12 + 64);
+            ws.r_count.reserve((n_chunks + 1) * 8);
+            if (ws.h_counts_cap < n_chunks + 1) {
+                if (ws.h_counts) cudaFreeHost(ws.h_counts);
+                ws.h_counts = nullptr;
+                CK(cudaMallocHost(reinterpret_cast<void**>(&ws.h_counts), (n_chunks + 1) * 2 * 8));
+                ws.h_counts_cap = (n_chunks + 1) * 2;
+            }
+            while (ws.ev_cnt.size() < n_chunks + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ws.ev_cnt.push_back(e);
+            }
+        }
+        // run-length pass over the codes [o0, o1) of one chunk (or of everything), count to the host
+        auto runs_pass = [&](uint64_t j, uint64_t set, uint64_t per, const uint64_t* d_codes, uint64_t o0, uint64_t o1,
+                             const uint64_t* d_code_off, uint64_t nc, cudaStream_t st) {
+            const uint64_t n = o1 - o0;
+            launch_runs(d_codes + o0, n, d_code_off, nc, o0, ws.r_start.as<uint8_t>() + set * per,
+                        ws.r_head.as<uint8_t>() + set * per, ws.r_rank.as<uint32_t>() + set * per,
+                        ws.r_head_at.as<uint32_t>() + set * per, static_cast<char*>(ws.r_tmp.p) + set * (ws.r_tmp.cap / 2 / 256 * 256),
+                        ws.r_tmp.cap / 2 / 256 * 256,
+                        ws.r_runs.as<uint8_t>() + o0 * 12, ws.r_count.as<unsigned long long>() + j, st);
+            f->stats.kernel_launches += 5;
+            CK(cudaMemcpyAsync(ws.h_counts + j, ws.r_count.as<unsigned long long>() + j, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ws.ev_cnt[j], st));
+        };
+        // once chunk j's count is known: its records to the caller's buffer, behind the earlier chunks'
+        auto runs_fetch = [&](uint64_t j, uint64_t o0, cudaStream_t st) {
+            CK(cudaEventSynchronize(ws.ev_cnt[j]));
+            const uint64_t n = ws.h_counts[j];
+            if (runs_done + n > sink.capacity || !sink.runs) {
+                runs_overflow = true;
+            } else if (n) {
+                CK(cudaMemcpyAsync(static_cast<char*>(sink.runs) + runs_done * 12, ws.r_runs.as<uint8_t>() + o0 * 12, n * 12,
+                                   cudaMemcpyDeviceToHost, st));
+            }
+            runs_done += n;
+        };
         if (!pipelined) {
             CK(cudaMemcpyAsync(ws.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
             ws.tile.reserve(query_tiled_ws_bytes(span));
@@ -469,13 +597,18 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
             run_kernels(f, b, s);
         } else {
             ws.ensure_pipeline();
-            const uint64_t n_chunks = cuts.size() - 1;
             std::vector<uint64_t> tile_at(n_chunks + 1, 0);
             for (uint64_t j = 0; j < n_chunks; ++j) {
                 uint64_t bytes = query_tiled_ws_bytes(offsets[cuts[j + 1]] - offsets[cuts[j]]);
                 tile_at[j + 1] = tile_at[j] + (bytes + 255) / 256 * 256;
             }
             ws.tile.reserve(tile_at[n_chunks]);
+            uint64_t per = 0;
+            if (want_runs) {
+                for (uint64_t j = 0; j < n_chunks; ++j)
+                    per = std::max<uint64_t>(per, code_offsets[cuts[j + 1]] - code_offsets[cuts[j]]);
+                per += 16;
+            }
             CK(cudaEventRecord(ws.ev_ready, s));
             for (uint64_t j = 0; j < n_chunks; ++j) {
                 cudaStream_t st = ws.cs[j & 1];
@@ -496,10 +629,16 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
                 bj.tile_ws_bytes = tile_at[j + 1] - tile_at[j];
                 run_kernels(f, bj, st);
                 const uint64_t o0 = code_offsets[c0], o1 = code_offsets[c1];
-                if (o1 > o0)
+                if (want_runs) {
+                    runs_pass(j, j & 1, per, ws.codes.as<uint64_t>(), o0, o1, bj.code_off, bj.n_contigs, st);
+                    // the previous chunk's records leave while this chunk computes
+                    if (j >= 1) runs_fetch(j - 1, code_offsets[cuts[j - 1]], ws.cs[(j - 1) & 1]);
+                } else if (o1 > o0) {
                     CK(cudaMemcpyAsync(codes + o0, ws.codes.as<uint64_t>() + o0, (o1 - o0) * 8,
                                        cudaMemcpyDeviceToHost, st));
+                }
             }
+            if (want_runs) runs_fetch(n_chunks - 1, code_offsets[cuts[n_chunks - 1]], ws.cs[(n_chunks - 1) & 1]);
             for (int i = 0; i < 2; ++i) {
                 CK(cudaEventRecord(ws.ev_done[i], ws.cs[i]));
                 CK(cudaStreamWaitEvent(s, ws.ev_done[i], 0));
@@ -511,7 +650,24 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         CK(cudaGetLastError());
         const uint64_t n_dirty = ws.h_status[1];
         f->stats.dirty_contigs = n_dirty;
+        // whole-stream run-length pass + copy (unpipelined batches; batches rewritten by the quirk path)
+        auto runs_whole = [&](const uint64_t* d_codes, uint64_t n) -> int {
+            runs_done = 0;
+            runs_overflow = false;
+            runs_pass(0, 0, 0, d_codes, 0, n, ws.code_off.as<uint64_t>(), n_contigs, s);
+            runs_fetch(0, 0, s);
+            CK(cudaStreamSynchronize(s));
+            CK(cudaGetLastError());
+            return LPHB_OK;
+        };
         if (n_dirty == 0) {
+            if (want_runs) {
+                if (!pipelined) runs_whole(ws.codes.as<uint64_t>(), total);
+                *sink.n_runs = runs_done;
+                if (runs_overflow) return fail(LPHB_E_CAPACITY, "runs buffer too small");
+                f->stats.d2h_bytes = runs_done * 12 + n_chunks * 8 + 32;
+                return LPHB_OK;
+            }
             if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
             if (total && !pipelined) {
                 CK(cudaMemcpyAsync(codes, ws.codes.p, total * 8, cudaMemcpyDeviceToHost, s));
@@ -564,7 +720,8 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         }
         code_offsets[n_contigs] = new_total;
         *n_codes = new_total;
-        if (new_total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+        if (!want_runs && new_total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+        if (want_runs && new_total >= (1ull << 31)) return fail(LPHB_E_ARG, "batch holds >= 2^31 codes: split it");
         ws.aux3.reserve((n_contigs + 1) * 8);
         ws.tmp.reserve(new_total * 8 + 64);
         CK(cudaMemcpyAsync(ws.aux3.p, src_off.data(), n_contigs * 8, cudaMemcpyHostToDevice, s));
@@ -573,6 +730,15 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
                         ws.codes2.as<uint64_t>(), ws.aux3.as<uint64_t>(), ws.dirty.as<uint8_t>(),
                         n_contigs, s);
         f->stats.kernel_launches += 1;
+        if (want_runs) {
+            reserve_runs(ws, new_total + 16);
+            ws.r_runs.reserve(new_total * 12 + 64);
+            runs_whole(ws.tmp.as<uint64_t>(), new_total);
+            *sink.n_runs = runs_done;
+            if (runs_overflow) return fail(LPHB_E_CAPACITY, "runs buffer too small");
+            f->stats.d2h_bytes = runs_done * 12 + n_contigs + list.size() * 8 + 40;
+            return LPHB_OK;
+        }
         if (new_total) CK(cudaMemcpyAsync(codes, ws.tmp.p, new_total * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
@@ -581,6 +747,80 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
     });
 }
 
+}  // namespace
+
+extern "C" {
+
+int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                      uint64_t* codes, uint64_t codes_capacity, uint64_t* code_offsets,
+                      uint64_t* n_codes) {
+    if (!f || !offsets || !code_offsets || !n_codes) return fail(LPHB_E_ARG, "null argument");
+    return query_stream_host(f, bases, offsets, n_contigs, codes, codes_capacity, code_offsets, n_codes, RunSink{});
+}
+
+int lphb_query_stream_runs(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                           void* runs, uint64_t runs_capacity, uint64_t* n_runs, uint64_t* code_offsets,
+                           uint64_t* n_codes) {
+    if (!f || !offsets || !code_offsets || !n_codes || !n_runs) return fail(LPHB_E_ARG, "null argument");
+    RunSink sink;
+    sink.runs = runs;
+    sink.capacity = runs ? runs_capacity : 0;
+    sink.n_runs = n_runs;
+    return query_stream_host(f, bases, offsets, n_contigs, nullptr, 0, code_offsets, n_codes, sink);
+}
+
+// Host side of the run-length form: the uint64_t vector the reference returns, bit for bit.  Pure
+// decoding of the device's output (no hashing happens here); `threads` host threads share the runs.
+int lphb_expand_runs(const void* runs, uint64_t n_runs, uint64_t* codes, uint64_t codes_capacity,
+                     uint64_t* n_codes, int threads) {
+    if ((n_runs && !runs) || !n_codes) return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        const unsigned char* p = static_cast<const unsigned char*>(runs);
+        if (threads < 1) threads = 1;
+        if (uint64_t(threads) > n_runs / 4096 + 1) threads = int(n_runs / 4096 + 1);
+        // where each thread's slice of runs starts in the output
+        std::vector<uint64_t> slice_at(size_t(threads) + 1, 0);
+        auto run_len = [&](uint64_t r) -> uint64_t {
+            int32_t n;
+            memcpy(&n, p + r * 12 + 8, 4);
+            return uint64_t(n < 0 ? -int64_t(n) : int64_t(n));
+        };
+        for (int t = 0; t < threads; ++t) {
+            uint64_t r0 = n_runs * uint64_t(t) / threads, r1 = n_runs * uint64_t(t + 1) / threads, sum = 0;
+            for (uint64_t r = r0; r < r1; ++r) sum += run_len(r);
+            slice_at[size_t(t) + 1] = slice_at[size_t(t)] + sum;
+        }
+        const uint64_t total = slice_at[size_t(threads)];
+        *n_codes = total;
+        if (total > codes_capacity) return fail(LPHB_E_CAPACITY, "codes buffer too small");
+        if (total && !codes) return fail(LPHB_E_ARG, "codes is null");
+        auto work = [&](int t) {
+            uint64_t at = slice_at[size_t(t)];
+            const uint64_t r0 = n_runs * uint64_t(t) / threads, r1 = n_runs * uint64_t(t + 1) / threads;
+            for (uint64_t r = r0; r < r1; ++r) {
+                uint64_t first;
+                int32_t n;
+                memcpy(&first, p + r * 12, 8);
+                memcpy(&n, p + r * 12 + 8, 4);
+                if (n >= 0) {
+                    for (int32_t j = 0; j < n; ++j) codes[at + uint64_t(j)] = first + uint64_t(j);
+                    at += uint64_t(n);
+                } else {
+                    for (int32_t j = 0; j < -n; ++j) codes[at + uint64_t(j)] = first - uint64_t(j);
+                    at += uint64_t(-int64_t(n));
+                }
+            }
+        };
+        if (threads == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        return LPHB_OK;
+    });
+}
 
 // ---- build-side scan ---------------------------------------------------------------------------
 }  // extern "C"

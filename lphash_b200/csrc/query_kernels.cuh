@@ -55,6 +55,13 @@ void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src
                      const uint64_t* src_b, const uint64_t* src_off, const uint8_t* from_b,
                      uint64_t n_contigs, cudaStream_t stream);
 
+// Run-length form of a code stream on the device (runs_kernels.cu): codes[0..n), n < 2^31 -> 12-byte
+// records {u64 first, i32 n} (n > 0 ascending, n < 0 descending), never across a contig start.
+uint64_t runs_tmp_bytes(uint64_t n);
+void launch_runs(const uint64_t* codes, uint64_t n, const uint64_t* code_off, uint64_t n_contigs, uint64_t o0,
+                 uint8_t* d_start, uint8_t* d_head, uint32_t* d_rank, uint32_t* d_head_at, void* d_tmp,
+                 uint64_t tmp_bytes, uint8_t* d_runs, unsigned long long* d_n_runs, cudaStream_t stream);
+
 // status[1] += number of set flags in dirty[0..n)
 void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status,
                         cudaStream_t stream);

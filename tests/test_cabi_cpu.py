@@ -87,3 +87,30 @@ def test_argument_errors():
     rc = L.lphb_scan_superkmers(0, 31, 40, 42, None, off.ctypes.data, 0, C.byref(mm), None, 0,
                                 C.byref(nrec), C.byref(nk))
     assert rc in (api.E_ARG, api.E_CUDA)
+
+
+def test_expand_runs_is_host_only_and_exact():
+    """lphb_expand_runs decodes run records on the host (no device needed): ascending, descending,
+    single codes, wrap-around mod 2^64, many threads, capacity error."""
+    import ctypes as C
+    rng = np.random.Generator(np.random.PCG64(5))
+    n_runs = 50000
+    runs = np.zeros(n_runs, dtype=api.RUN_DTYPE)
+    runs["first"] = rng.integers(0, 1 << 63, size=n_runs, dtype=np.uint64)
+    runs["n"] = rng.integers(-40, 41, size=n_runs)
+    runs["n"][runs["n"] == 0] = 1
+    runs["first"][0], runs["n"][0] = 2, -5           # 2, 1, 0, 2^64-1, 2^64-2 (mod 2^64 like the reference)
+    runs["first"][1], runs["n"][1] = (1 << 64) - 2, 4
+    want = []
+    for f, n in zip(runs["first"].tolist(), runs["n"].tolist()):
+        step = 1 if n > 0 else -1
+        want.extend(((f + step * j) & 0xFFFFFFFFFFFFFFFF) for j in range(abs(n)))
+    want = np.array(want, dtype=np.uint64)
+    for threads in (1, 3, 16):
+        got = api.expand_runs(runs, threads=threads)
+        assert np.array_equal(got, want), threads
+    assert len(api.expand_runs(runs[:0])) == 0
+    small = np.empty(3, dtype=np.uint64)
+    n = C.c_uint64(0)
+    rc = api.lib().lphb_expand_runs(runs.ctypes.data, n_runs, small.ctypes.data, 3, C.byref(n), 1)
+    assert rc == api.E_CAPACITY and n.value == len(want)

@@ -25,8 +25,10 @@ def kseq_records(data: bytes) -> list[bytes]:
         p += 1
         return c
 
-    def line(strip=True):
-        """rest of the current line (KS_SEP_LINE): without the newline and a trailing CR; None at EOF"""
+    def line(acc=2):
+        """rest of the current line (KS_SEP_LINE) appended to a string that already holds `acc`
+        characters: without the newline, and without a trailing CR if the string is then longer than
+        one character (ks_getuntil2: `str->l > 1 && str->s[str->l-1] == '\\r'`); None at EOF"""
         nonlocal p
         if p >= n:
             return None
@@ -35,7 +37,7 @@ def kseq_records(data: bytes) -> list[bytes]:
             e = n
         s = data[p:e]
         p = min(e + 1, n)
-        if strip and s.endswith(b"\r"):
+        if acc + len(s) > 1 and (s.endswith(b"\r") if s else False):
             s = s[:-1]
         return s
 
@@ -55,11 +57,11 @@ def kseq_records(data: bytes) -> list[bytes]:
         while c >= 0 and c not in (ord(">"), ord("+"), ord("@")):
             if c != ord("\n"):
                 seq.append(c)
-                rest = line()
+                rest = line(len(seq))
                 if rest is not None:
                     seq += rest
-                if seq.endswith(b"\r"):  # a line that was only "X\r"
-                    pass
+                    if not rest and len(seq) > 1 and seq.endswith(b"\r"):
+                        del seq[-1]  # the line was only "\r" and the sequence is longer than it
             c = getc()
         if c in (ord(">"), ord("@")):
             last = c
@@ -75,7 +77,7 @@ def kseq_records(data: bytes) -> list[bytes]:
             break  # -2: no quality string
         qual = 0
         while True:
-            q = line()
+            q = line(qual)
             if q is None:
                 break
             qual += len(q)
@@ -91,6 +93,9 @@ def kseq_records(data: bytes) -> list[bytes]:
 CASES = {
     "fasta_multiline": b">a desc\nACGT\nACG\n\nAC\n>b\n>c\nNNNN\nacgu\n>d",
     "fasta_crlf": b">a\r\nACGT\r\nAC\r\n>b\r\nGG\r\n",
+    # kseq keeps the CR of a lone "\r\n" line when it is the FIRST sequence line (accumulated length 1)
+    "fasta_crlf_blank_first": b">a\r\n\r\nACGT\r\n\r\nAC\r\n>b\r\n\r\n>c\r\nG\r\n",
+    "fastq_crlf_blank_first": b"@r1\r\n\r\nACG\r\n+\r\n\r\nIII\r\n@r2\r\nA\r\n+\r\nI\r\n",
     "fasta_leading_junk": b"junk\n\n>x\nAC\n",
     "fastq_4line": b"@r1\nACGTN\n+\nIIIII\n@r2 c\nAC\n+r2\nII\n",
     "fastq_multiline": b"@r1\nACGT\nAC\n+\nIII\nIII\n@r2\nGG\n+\n@@\n@r3\nT\n+\nI\n",

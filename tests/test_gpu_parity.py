@@ -361,3 +361,44 @@ def test_small_probe_chunks_variant():
     env = dict(os.environ, LPHASH_B200_LIB=lib)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- run-length form of the codes (lphb_query_stream_runs) -----------------------------------------
+
+@pytest.mark.parametrize("chunk", [0, 900, 1 << 16])
+def test_run_length_form_expands_to_the_same_codes(golden, handles, chunk, monkeypatch):
+    """Members, non-members, colliding minimizers, short contigs and the non-ACGT quirk: the run
+    records expand to exactly the vector lphb_query_stream returns, for one-shot and chunk-pipelined
+    batches; runs never cross a contig."""
+    f = handles(golden.name)
+    monkeypatch.setenv("LPHB_CHUNK_BASES", str(chunk))
+    for bases, offsets, want, want_off in [(golden.q_bases, golden.q_offsets, golden.q_codes, golden.q_code_offsets),
+                                           (golden.index_bases, golden.index_offsets, None, None)]:
+        if want is None:
+            want, want_off = f.query_batch(bases, offsets)
+        runs, code_off, n_codes = f.query_batch_runs(bases, offsets)
+        assert n_codes == len(want) and np.array_equal(code_off, want_off)
+        assert np.array_equal(api.expand_runs(runs, threads=4), want)
+        ends = np.cumsum(np.abs(runs["n"].astype(np.int64)))
+        assert np.isin(want_off[1:][np.diff(want_off) > 0], ends).all()  # every contig ends a run
+    # compactness on the all-member set: about one run per super-k-mer (2 / (k - m + 2) per k-mer), plus
+    # single-code runs for the k-mers of colliding minimizers (frequent in these tiny indexes)
+    assert len(runs) < (2.0 / (golden.k - golden.m + 2) + 0.35) * n_codes
+
+
+def test_run_length_form_capacity_and_count_only(handles):
+    g = load_golden("k31_m20_u64")
+    f = handles(g.name)
+    runs, _, n_codes = f.query_batch_runs(g.index_bases, g.index_offsets)
+    small = np.empty(5, dtype=api.RUN_DTYPE)
+    with pytest.raises(api.LphashError) as e:
+        f.query_batch_runs(g.index_bases, g.index_offsets, out=small)
+    assert e.value.code == api.E_CAPACITY
+    n_runs, total = C.c_uint64(0), C.c_uint64(0)
+    off = np.empty(len(g.index_offsets), dtype=np.uint64)
+    bases = np.ascontiguousarray(g.index_bases)
+    offsets = np.ascontiguousarray(g.index_offsets, dtype=np.uint64)
+    rc = api.lib().lphb_query_stream_runs(f._h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, None, 0,
+                                          C.byref(n_runs), off.ctypes.data, C.byref(total))
+    assert rc == api.E_CAPACITY or rc == 0
+    assert n_runs.value == len(runs) and total.value == n_codes
