@@ -129,11 +129,26 @@ int lphb_mphf_dirty_flags(const lphb_mphf* f, const uint8_t** d_flags, uint64_t*
  * Replaces the loop over minimizer::from_string (include/minimizer.hpp:11-170; caller
  * src/partitioned_mphf.cpp:70-77) for a batch of contigs.  records receives packed 18-byte
  * mm_record_t {u64 itself, u64 id, u8 p1, u8 size} (include/constants.hpp:26-33) in scan order;
- * mm_count is the running global m-mer ordinal (in: value before the batch, out: after).        */
+ * mm_count is the running global m-mer ordinal (in: value before the batch, out: after).
+ * Input contract: ACGT/acgt (U/u) only, the k-mer sets lphash is built from (BCALM2/UST unitigs; the
+ * reference documents its build as taking "valid k-mers only", src/parser_build.cpp:13-16).  A batch
+ * with any other byte is refused with LPHB_E_ARG and produces nothing; the reference would flush the
+ * open super-k-mer at the byte and go on (include/minimizer.hpp:138-151), which is not reproduced.
+ * A batch must hold fewer than 2^32 k-mers and span fewer than 2^32 bases.                         */
 int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
                          const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,
                          void* records, uint64_t records_capacity, uint64_t* n_records,
                          uint64_t* n_kmers);
+
+/* Device-resident variant: d_bases / d_offsets are device pointers on `device` (d_bases indexed by
+ * the offsets), h_offsets the host copy of the offsets.  Synchronous.  *d_records receives a DEVICE
+ * pointer to the packed records (scan order), owned by the library and valid until the next scan
+ * call on the device or lphb_scan_release; *kernel_ms (optional) the CUDA-event time of the
+ * record-producing kernels.                                                                        */
+int lphb_scan_superkmers_device(int device, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases,
+                                const uint64_t* d_offsets, const uint64_t* h_offsets, uint64_t n_contigs,
+                                uint64_t* mm_count, const void** d_records, uint64_t* n_records,
+                                uint64_t* n_kmers, double* kernel_ms);
 
 /* The two build-side entry points keep their device workspace per device between calls (a caller
  * streaming batches does not pay allocation on every batch); this frees it.                      */
@@ -170,6 +185,8 @@ int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
 
 /* ---- pinned host memory (optional; makes the copies inside lphb_query_stream asynchronous) -- */
 int lphb_host_alloc(void** ptr, uint64_t nbytes);
+/* synchronous copy of a library-owned device buffer (e.g. *d_records of lphb_scan_superkmers_device) */
+int lphb_copy_to_host(int device, void* dst, const void* d_src, uint64_t nbytes);
 int lphb_host_free(void* ptr);
 
 /* Counters for the last lphb_query_stream* call on the handle (kernel launches, device ms). */

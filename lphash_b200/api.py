@@ -51,7 +51,8 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_mphf_load_memory", "lphb_mphf_free", "lphb_mphf_info", "lphb_query_stream",
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
            "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify",
-           "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags"]
+           "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags",
+           "lphb_scan_superkmers_device", "lphb_copy_to_host"]
 
 _lib = None
 
@@ -83,10 +84,13 @@ def lib() -> C.CDLL:
                                        u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_colliding_kmers.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p,
                                        u64, i32, p, u64, C.POINTER(u64)]
+    L.lphb_scan_superkmers_device.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, p, u64, C.POINTER(u64), C.POINTER(p),
+                                              C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.lphb_classify.argtypes = [i32, p, u64, p, u64, C.POINTER(u64), p, u64, C.POINTER(u64)]
     L.lphb_scan_release.argtypes = [i32]
     L.lphb_scan_classify.argtypes = [i32, C.c_uint32, C.c_uint32, u64, p, p, u64, C.POINTER(u64), p, u64,
                                      C.POINTER(u64), p, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.lphb_copy_to_host.argtypes = [i32, p, p, u64]
     L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
     L.lphb_host_free.argtypes = [p]
     for name in EXPORTS:
@@ -245,6 +249,25 @@ def scan_superkmers(bases, offsets, k: int, m: int, seed: int = 42, mm_count: in
     _check(lib().lphb_scan_superkmers(device, k, m, seed, bases.ctypes.data, offsets.ctypes.data, n,
                                       C.byref(mm), rec.ctypes.data, cap, C.byref(nrec), C.byref(nk)))
     return rec[: nrec.value], nk.value, mm.value
+
+
+def scan_superkmers_device(d_bases: int, d_offsets: int, h_offsets, k: int, m: int, seed: int = 42,
+                           mm_count: int = 0, device: int = 0, fetch: bool = True):
+    """lphb_scan_superkmers_device: bases / offsets already on the device (raw pointers).  Returns
+    (records or None, n_records, n_kmers, mm_count_out, kernel_ms)."""
+    h_offsets = np.ascontiguousarray(h_offsets, dtype=np.uint64)
+    mm = C.c_uint64(mm_count)
+    ptr = C.c_void_p()
+    nrec, nk, ms = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+    _check(lib().lphb_scan_superkmers_device(device, k, m, seed, d_bases, d_offsets, h_offsets.ctypes.data,
+                                             len(h_offsets) - 1, C.byref(mm), C.byref(ptr), C.byref(nrec), C.byref(nk),
+                                             C.byref(ms)))
+    rec = None
+    if fetch:
+        rec = np.empty(nrec.value, dtype=RECORD_DTYPE)
+        if nrec.value:
+            _check(lib().lphb_copy_to_host(device, rec.ctypes.data, ptr, nrec.value * 18))
+    return rec, nrec.value, nk.value, mm.value, ms.value
 
 
 TRIPLET_DTYPE = np.dtype([("itself", "<u8"), ("p1", "u1"), ("size", "u1")])  # mm_triplet_t

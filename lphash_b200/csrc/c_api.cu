@@ -405,6 +405,15 @@ int lphb_host_alloc(void** ptr, uint64_t nbytes) {
     return LPHB_OK;
 }
 
+int lphb_copy_to_host(int device, void* dst, const void* d_src, uint64_t nbytes) {
+    if (nbytes && (!dst || !d_src)) return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        if (nbytes) CK(cudaMemcpy(dst, d_src, nbytes, cudaMemcpyDeviceToHost));
+        return LPHB_OK;
+    });
+}
+
 int lphb_host_free(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
     return LPHB_OK;
@@ -827,29 +836,43 @@ int lphb_expand_runs(const void* runs, uint64_t n_runs, uint64_t* codes, uint64_
 
 namespace {
 
-// Per-call device buffers of the scan pipeline (freed on scope exit).
+// Device workspace of the build-side scan, kept per device between calls.
 struct ScanSession {
-    DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, head_at, tmp, status, tile_ws;
+    DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, start_pos, tmp, status, tile_ws;
     cudaStream_t s = nullptr;
     ScanBatch b{};
     uint64_t n_records = 0, n_kmers = 0, tmp_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the record-producing kernels of the last scan
+    double kernel_ms = 0;
     ~ScanSession() {
         for (DevBuf* d : {&bases, &offsets, &code_off, &id_base, &dirty, &head, &pos, &rank, &records,
-                          &head_at, &tmp, &status, &tile_ws})
+                          &start_pos, &tmp, &status, &tile_ws})
             d->release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (s) cudaStreamDestroy(s);
     }
 };
 
 // The scan entry points have no handle: their device workspace (a few bytes per base) is kept per
 // device between calls, so that a caller streaming batches does not pay cudaMalloc / cudaFree
-// (both synchronizing) on every batch.  One scan at a time per process; lphb_scan_release frees it.
-std::mutex g_scan_mu;
-ScanSession* g_scan[64] = {};
-ScanSession& scan_session(int device) {
+// (both synchronizing) on every batch.  One mutex PER DEVICE: scans on different GPUs driven from
+// different host threads run concurrently, scans on one GPU take turns; lphb_scan_release frees.
+struct ClassifySession;
+struct DeviceSessions {
+    std::mutex mu;
+    ScanSession* scan = nullptr;
+    ClassifySession* classify = nullptr;
+};
+DeviceSessions g_dev[64];
+DeviceSessions& device_sessions(int device) {
     if (device < 0 || device >= 64) throw std::invalid_argument("device index out of range");
-    if (!g_scan[device]) g_scan[device] = new ScanSession();
-    return *g_scan[device];
+    return g_dev[device];
+}
+ScanSession& scan_session(int device) {
+    DeviceSessions& d = device_sessions(device);
+    if (!d.scan) d.scan = new ScanSession();
+    return *d.scan;
 }
 
 // LPHB_SCAN_TRACE=1: per-stage wall times of the scan on stderr (each mark synchronizes the stream)
@@ -865,7 +888,111 @@ struct ScanTrace {
     }
 };
 
-// Passes 1-2 of the scan for a host batch; leaves records / rank / head_at on the device.
+// The scan of one batch whose bases and offsets are ALREADY on the device (d_bases indexed by the
+// offsets, i.e. d_bases + offsets[0] is the first base): leaves the records (scan order) and the
+// stream position of every record's first k-mer in the session, returns after the device finished.
+// Instantiated (k, m): one fused kernel (query_tiled.cu, kScan form); others: the generic passes.
+int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases,
+                    const uint64_t* d_offsets, const uint64_t* offsets, uint64_t n_contigs, uint64_t mm_count_in,
+                    uint64_t* mm_count_out, ScanTrace& tr) {
+    cudaStream_t s = S.s;
+    const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
+    const uint64_t n_kmers = S.n_kmers;
+    S.code_off.reserve((n_contigs + 1) * 8);
+    S.id_base.reserve((n_contigs + 1) * 8);
+    S.dirty.reserve(n_contigs + 8);
+    S.status.reserve(64);
+    S.records.reserve(n_kmers * 18 + 64);       // capacity: one record per k-mer (low-complexity worst case)
+    S.start_pos.reserve((n_kmers + 2) * 4);
+    const bool tiled = scan_tiled_available(k, m);
+    uint64_t t1 = tiled ? 0 : head_ranks_tmp_bytes(n_kmers > n_contigs ? n_kmers : n_contigs);
+    uint64_t t2 = code_offsets_tmp_bytes(n_contigs);
+    uint64_t t3 = head_ranks_tmp_bytes(n_contigs);  // the m-mer ordinal scan over contigs
+    S.tmp_bytes = std::max(std::max(t1, t2), t3);
+    S.tmp.reserve(S.tmp_bytes);
+    if (!tiled) {
+        S.head.reserve(n_kmers + 8);
+        S.pos.reserve(n_kmers + 8);
+        S.rank.reserve((n_kmers + 2) * 4);
+    }
+    S.tile_ws.reserve(query_tiled_ws_bytes(span));
+    if (!S.ev0) {
+        CK(cudaEventCreate(&S.ev0));
+        CK(cudaEventCreate(&S.ev1));
+    }
+    tr.mark(s, "device allocations");
+    CK(cudaMemsetAsync(S.dirty.p, 0, n_contigs + 8, s));
+    auto* st = S.status.as<unsigned long long>();
+    CK(cudaMemsetAsync(st, 0, 64, s));
+    launch_code_offsets(d_offsets, n_contigs, k, S.code_off.as<uint64_t>(), st, S.tmp.p, S.tmp_bytes, s);
+    launch_id_base(d_offsets, n_contigs, m, mm_count_in, S.id_base.as<uint64_t>(), S.tmp.p, S.tmp_bytes, s);
+    ScanBatch& b = S.b;
+    b.bases = d_bases;
+    b.offsets = d_offsets;
+    b.code_off = S.code_off.as<uint64_t>();
+    b.id_base = S.id_base.as<uint64_t>();
+    b.n_contigs = n_contigs;
+    b.first_base = first;
+    b.end_base = first + span;
+    b.n_kmers = n_kmers;
+    b.k = k;
+    b.m = m;
+    b.seed = seed;
+    b.dirty = S.dirty.as<uint8_t>();
+    CK(cudaEventRecord(S.ev0, s));
+    unsigned long long h_nrec = 0;
+    if (tiled) {
+        DevBatch qb{};
+        qb.bases = b.bases;
+        qb.offsets = b.offsets;
+        qb.code_off = b.code_off;
+        qb.n_contigs = n_contigs;
+        qb.first_base = b.first_base;
+        qb.end_base = b.end_base;
+        qb.dirty = b.dirty;
+        qb.status = st;
+        qb.tile_ws = S.tile_ws.p;
+        qb.tile_ws_bytes = S.tile_ws.cap;
+        if (!launch_scan_records_tiled(k, m, seed, qb, b.id_base, S.records.as<uint8_t>(), S.start_pos.as<uint32_t>(),
+                                       st + 2, s))
+            return fail(LPHB_E_ARG, "scan: batch too large for one launch");
+        CK(cudaEventRecord(S.ev1, s));
+        launch_count_dirty(b.dirty, n_contigs, st, s);
+        tr.mark(s, "fused scan kernel");
+    } else {
+        CK(cudaMemsetAsync(S.head.p, 0, n_kmers + 8, s));
+        launch_scan_heads(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), s);
+        launch_count_dirty(b.dirty, n_contigs, st, s);
+        launch_head_ranks(S.head.as<uint8_t>(), n_kmers, S.rank.as<uint32_t>(), S.tmp.p, S.tmp_bytes, s);
+        tr.mark(s, "generic pass 1 + ranks");
+    }
+    unsigned long long h_st[3] = {0, 0, 0};
+    uint32_t n_rec32 = 0;
+    CK(cudaMemcpyAsync(h_st, st, sizeof(h_st), cudaMemcpyDeviceToHost, s));
+    if (!tiled) CK(cudaMemcpyAsync(&n_rec32, S.rank.as<uint32_t>() + n_kmers, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h_st[1] != 0)
+        return fail(LPHB_E_ARG,
+                    "build input contains non-ACGT bytes (the reference's build requires valid "
+                    "k-mers only, src/parser_build.cpp:13-16); not supported by the GPU scan");
+    h_nrec = tiled ? h_st[2] : n_rec32;
+    S.n_records = h_nrec;
+    if (!tiled) {
+        launch_scan_emit(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), S.rank.as<uint32_t>(),
+                         S.records.as<uint8_t>(), S.start_pos.as<uint32_t>(), s);
+        CK(cudaEventRecord(S.ev1, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        tr.mark(s, "generic pass 2 (emit records)");
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) S.kernel_ms = ms; else cudaGetLastError();
+    (void)mm_count_out;
+    return LPHB_OK;
+}
+
+// Validates a host batch, moves it to the device and scans it.
 int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
              const uint64_t* offsets, uint64_t n_contigs, uint64_t mm_count_in,
              uint64_t* mm_count_out) {
@@ -886,86 +1013,15 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     if (!bases) return fail(LPHB_E_ARG, "bases is null");
     cudaStream_t s = S.s;
     const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
+    if (span >= (1ull << 32)) return fail(LPHB_E_ARG, "batch spans >= 2^32 bases: split it");
     S.bases.reserve(span + 64);
     S.offsets.reserve((n_contigs + 1) * 8);
-    S.code_off.reserve((n_contigs + 1) * 8);
-    S.id_base.reserve((n_contigs + 1) * 8);
-    S.dirty.reserve(n_contigs + 8);
-    S.head.reserve(n_kmers + 8);
-    S.pos.reserve(n_kmers + 8);
-    S.rank.reserve((n_kmers + 2) * 4);
-    S.status.reserve(64);
-    uint64_t t1 = head_ranks_tmp_bytes(n_kmers > n_contigs ? n_kmers : n_contigs);
-    uint64_t t2 = code_offsets_tmp_bytes(n_contigs);
-    uint64_t t3 = exclusive_u32_tmp_bytes(n_kmers);
-    S.tmp_bytes = t1 > t2 ? t1 : t2;
-    if (t3 > S.tmp_bytes) S.tmp_bytes = t3;
-    S.tmp.reserve(S.tmp_bytes);
     ScanTrace tr;
-    tr.mark(s, "device allocations");
     CK(cudaMemcpyAsync(S.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(S.offsets.p, offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
     tr.mark(s, "H2D bases + offsets");
-    CK(cudaMemsetAsync(S.dirty.p, 0, n_contigs + 8, s));
-    CK(cudaMemsetAsync(S.head.p, 0, n_kmers + 8, s));
-    auto* st = S.status.as<unsigned long long>();
-    launch_code_offsets(S.offsets.as<uint64_t>(), n_contigs, k, S.code_off.as<uint64_t>(), st, S.tmp.p,
-                        S.tmp_bytes, s);
-    launch_id_base(S.offsets.as<uint64_t>(), n_contigs, m, mm_count_in, S.id_base.as<uint64_t>(),
-                   S.tmp.p, S.tmp_bytes, s);
-    ScanBatch& b = S.b;
-    b.bases = S.bases.as<char>() - first;
-    b.offsets = S.offsets.as<uint64_t>();
-    b.code_off = S.code_off.as<uint64_t>();
-    b.id_base = S.id_base.as<uint64_t>();
-    b.n_contigs = n_contigs;
-    b.first_base = first;
-    b.end_base = first + span;
-    b.n_kmers = n_kmers;
-    b.k = k;
-    b.m = m;
-    b.seed = seed;
-    b.dirty = S.dirty.as<uint8_t>();
-    {   // pass 1: the tiled kernel where (k, m) is instantiated, else the generic one
-        DevBatch qb{};
-        qb.bases = b.bases;
-        qb.offsets = b.offsets;
-        qb.code_off = b.code_off;
-        qb.n_contigs = n_contigs;
-        qb.first_base = b.first_base;
-        qb.end_base = b.end_base;
-        qb.codes = reinterpret_cast<uint64_t*>(S.pos.p);  // one byte per k-mer (see launch_scan_pos_tiled)
-        qb.dirty = b.dirty;
-        qb.status = st;
-        S.tile_ws.reserve(query_tiled_ws_bytes(span));
-        qb.tile_ws = S.tile_ws.p;
-        qb.tile_ws_bytes = query_tiled_ws_bytes(span);
-        if (launch_scan_pos_tiled(k, m, seed, qb, s)) launch_heads_from_pos(b, S.pos.as<uint8_t>(), S.head.as<uint8_t>(), s);
-        else launch_scan_heads(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), s);
-    }
-    tr.mark(s, "offset scans + pass 1 (heads)");
-    launch_count_dirty(b.dirty, n_contigs, st, s);
-    launch_head_ranks(S.head.as<uint8_t>(), n_kmers, S.rank.as<uint32_t>(), S.tmp.p, S.tmp_bytes, s);
-    unsigned long long h_st[2] = {0, 0};
-    uint32_t n_rec32 = 0;
-    CK(cudaMemcpyAsync(h_st, st, sizeof(h_st), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&n_rec32, S.rank.as<uint32_t>() + n_kmers, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
-    if (h_st[1] != 0)
-        return fail(LPHB_E_ARG,
-                    "build input contains non-ACGT bytes (the reference's build requires valid "
-                    "k-mers only, src/parser_build.cpp:13-16); not supported by the GPU scan yet");
-    tr.mark(s, "head ranks");
-    S.n_records = n_rec32;
-    S.records.reserve(S.n_records * 18 + 64);
-    S.head_at.reserve((S.n_records + 1) * 4);
-    tr.mark(s, "record allocations");
-    launch_scan_emit(b, S.head.as<uint8_t>(), S.pos.as<uint8_t>(), S.rank.as<uint32_t>(),
-                     S.records.as<uint8_t>(), S.head_at.as<uint32_t>(), s);
-    CK(cudaGetLastError());
-    tr.mark(s, "pass 2 (emit records)");
-    return LPHB_OK;
+    return run_scan_device(S, k, m, seed, S.bases.as<char>() - first, S.offsets.as<uint64_t>(), offsets, n_contigs,
+                           mm_count_in, mm_count_out, tr);
 }
 
 struct ClassifySession {
@@ -975,18 +1031,17 @@ struct ClassifySession {
             d->release();
     }
 };
-ClassifySession* g_classify[64] = {};
 ClassifySession& classify_session(int device) {
-    if (device < 0 || device >= 64) throw std::invalid_argument("device index out of range");
-    if (!g_classify[device]) g_classify[device] = new ClassifySession();
-    return *g_classify[device];
+    DeviceSessions& d = device_sessions(device);
+    if (!d.classify) d.classify = new ClassifySession();
+    return *d.classify;
 }
 
 // Sort by minimizer + classify of n records that are already on the device (stream s); results to host.
 int classify_device(const uint8_t* d_rec, uint64_t n, void* triplets, uint64_t triplets_capacity,
                     uint64_t* n_triplets, uint64_t* ids, uint64_t ids_capacity, uint64_t* n_ids,
                     cudaStream_t s) {
-    // workspace kept per device between calls (freed by lphb_scan_release); callers hold g_scan_mu
+    // workspace kept per device between calls (freed by lphb_scan_release); callers hold the device's mutex
     int dev = 0;
     CK(cudaGetDevice(&dev));
     ClassifySession& cs = classify_session(dev);
@@ -1038,7 +1093,7 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     if (!offsets || !mm_count || !n_records || !n_kmers) return fail(LPHB_E_ARG, "null argument");
     return guarded([&]() -> int {
         DeviceGuard g(device);
-        std::lock_guard<std::mutex> lock(g_scan_mu);
+        std::lock_guard<std::mutex> lock(device_sessions(device).mu);
         ScanSession& S = scan_session(device);
         uint64_t mm_out = *mm_count;
         int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
@@ -1056,15 +1111,60 @@ int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     });
 }
 
+int lphb_scan_superkmers_device(int device, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases,
+                                const uint64_t* d_offsets, const uint64_t* h_offsets, uint64_t n_contigs,
+                                uint64_t* mm_count, const void** d_records, uint64_t* n_records, uint64_t* n_kmers,
+                                double* kernel_ms) {
+    if (!h_offsets || !d_offsets || !mm_count || !d_records || !n_records || !n_kmers)
+        return fail(LPHB_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        DeviceGuard g(device);
+        std::lock_guard<std::mutex> lock(device_sessions(device).mu);
+        ScanSession& S = scan_session(device);
+        if (m == 0 || m > 31 || k < m || k > 63) return fail(LPHB_E_ARG, "need 1 <= m <= 31, m <= k <= 63");
+        uint64_t nk = 0, nm = 0;
+        for (uint64_t c = 0; c < n_contigs; ++c) {
+            if (h_offsets[c + 1] < h_offsets[c]) return fail(LPHB_E_ARG, "offsets must be non-decreasing");
+            uint64_t len = h_offsets[c + 1] - h_offsets[c];
+            nk += len >= k ? len - k + 1 : 0;
+            nm += len >= m ? len - m + 1 : 0;
+        }
+        if (nk >= (1ull << 32) || (n_contigs && h_offsets[n_contigs] - h_offsets[0] >= (1ull << 32)))
+            return fail(LPHB_E_ARG, "batch holds >= 2^32 k-mers or bases: split it");
+        S.n_kmers = nk;
+        S.n_records = 0;
+        *n_kmers = nk;
+        *n_records = 0;
+        *d_records = nullptr;
+        if (kernel_ms) *kernel_ms = 0;
+        if (!S.s) CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
+        uint64_t mm_out = *mm_count + nm;
+        if (n_contigs && nk) {
+            if (!d_bases) return fail(LPHB_E_ARG, "d_bases is null");
+            CK(cudaDeviceSynchronize());  // the caller's buffers may still be written on other streams
+            ScanTrace tr;
+            int rc = run_scan_device(S, k, m, seed, d_bases, d_offsets, h_offsets, n_contigs, *mm_count, &mm_out, tr);
+            if (rc != LPHB_OK) return rc;
+            *d_records = S.records.p;
+            *n_records = S.n_records;
+            if (kernel_ms) *kernel_ms = S.kernel_ms;
+        }
+        *mm_count = mm_out;
+        return LPHB_OK;
+    });
+}
+
 int lphb_scan_release(int device) {
     return guarded([&]() -> int {
-        std::lock_guard<std::mutex> lock(g_scan_mu);
-        if (device < 0 || device >= 64 || (!g_scan[device] && !g_classify[device])) return LPHB_OK;
+        if (device < 0 || device >= 64) return LPHB_OK;
+        DeviceSessions& d = device_sessions(device);
+        std::lock_guard<std::mutex> lock(d.mu);
+        if (!d.scan && !d.classify) return LPHB_OK;
         DeviceGuard g(device);
-        delete g_scan[device];
-        g_scan[device] = nullptr;
-        delete g_classify[device];
-        g_classify[device] = nullptr;
+        delete d.scan;
+        d.scan = nullptr;
+        delete d.classify;
+        d.classify = nullptr;
         return LPHB_OK;
     });
 }
@@ -1079,7 +1179,7 @@ int lphb_classify(int device, const void* records, uint64_t n_records, void* tri
         *n_triplets = 0;
         *n_ids = 0;
         if (n_records == 0) return LPHB_OK;
-        std::lock_guard<std::mutex> lock(g_scan_mu);
+        std::lock_guard<std::mutex> lock(device_sessions(device).mu);
         DevBuf& rec = classify_session(device).rec;
         struct Free {
             cudaStream_t s = nullptr;
@@ -1102,7 +1202,7 @@ int lphb_scan_classify(int device, uint32_t k, uint32_t m, uint64_t seed, const 
     if (!offsets || !mm_count || !n_triplets || !n_ids || !n_kmers) return fail(LPHB_E_ARG, "null argument");
     return guarded([&]() -> int {
         DeviceGuard g(device);
-        std::lock_guard<std::mutex> lock(g_scan_mu);
+        std::lock_guard<std::mutex> lock(device_sessions(device).mu);
         ScanSession& S = scan_session(device);
         uint64_t mm_out = *mm_count;
         int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
@@ -1129,7 +1229,7 @@ int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
     if (k > uint32_t(kmer_bits / 2 - 1)) return fail(LPHB_E_ARG, "k too large for this kmer_t");
     return guarded([&]() -> int {
         DeviceGuard g(device);
-        std::lock_guard<std::mutex> lock(g_scan_mu);
+        std::lock_guard<std::mutex> lock(device_sessions(device).mu);
         ScanSession& S = scan_session(device);
         uint64_t mm_out = *mm_count;
         int rc = run_scan(S, k, m, seed, bases, offsets, n_contigs, *mm_count, &mm_out);
@@ -1163,9 +1263,8 @@ int lphb_colliding_kmers(int device, uint32_t k, uint32_t m, uint64_t seed, cons
             if (!kmers) return fail(LPHB_E_ARG, "kmers is null");
             const uint64_t bytes = total * uint64_t(kmer_bits / 8);
             out.reserve(bytes + 64);
-            launch_colliding_emit(S.b, S.rank.as<uint32_t>(), S.head_at.as<uint32_t>(),
-                                  take.as<uint32_t>(), out_off.as<uint64_t>(), kmer_bits,
-                                  out.as<uint8_t>(), s);
+            launch_colliding_emit(S.b, S.n_records, S.start_pos.as<uint32_t>(), take.as<uint32_t>(),
+                                  out_off.as<uint64_t>(), kmer_bits, out.as<uint8_t>(), s);
             CK(cudaMemcpyAsync(kmers, out.p, bytes, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             CK(cudaGetLastError());

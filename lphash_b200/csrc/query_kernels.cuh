@@ -37,11 +37,16 @@ void launch_query_generic(DevImage const& img, DevBatch const& b, cudaStream_t s
 // of them (the caller then uses the generic kernel).
 bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream);
 
-// Build-side form of the tiled kernel (minimizer::from_string): writes, for every valid k-mer start
-// in dense order (b.code_off layout), the offset of its minimizer inside the k-mer as one byte at
-// reinterpret_cast<uint8_t*>(b.codes); flags contigs with non-ACGT bytes in b.dirty.  Returns false
-// if (k, m) is not instantiated (the caller then uses the generic scan kernel).
-bool launch_scan_pos_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, cudaStream_t stream);
+// Build-side form of the tiled kernel (minimizer::from_string): writes the packed 18-byte mm_record_t
+// stream of the batch in scan order to d_records (capacity: one record per k-mer start), the stream
+// position (relative to b.first_base) of every record's first k-mer to d_start_pos, and the number of
+// records to *d_n_records; flags contigs with non-ACGT bytes in b.dirty (their records are then
+// meaningless).  d_id_base[c] = m-mer ordinal of contig c's first m-mer.  b.codes / b.code_off are not
+// used.  Returns false if (k, m) is not instantiated (the caller then uses the generic scan kernels).
+bool launch_scan_records_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, const uint64_t* d_id_base,
+                               uint8_t* d_records, uint32_t* d_start_pos, unsigned long long* d_n_records,
+                               cudaStream_t stream);
+bool scan_tiled_available(uint32_t k, uint32_t m);
 
 // Exact sequential emulation of the reference's streaming loop for contigs that contain
 // non-ACGT bytes (one thread per listed contig).  out_off[j] = where contig list[j] may write

@@ -129,6 +129,12 @@ struct TileArgs {
     int64_t pos0;               // stream position of abase (may be < first_base by < 16)
     const TileRec* recs;        // per tile
     uint32_t n_tiles;
+    // build-side (scan) form only
+    uint8_t* records;           // packed 18-byte mm_record_t, scan order
+    uint32_t* start_pos;        // per record: stream position of its first k-mer, relative to first_base
+    uint64_t* desc;             // 2 words per tile (aggregate, inclusive prefix), zeroed before the launch
+    const uint64_t* id_base;    // per contig: m-mer ordinal of its first m-mer
+    unsigned long long* n_records;  // total number of records (written by the last tile)
 };
 
 // 4 ASCII bytes -> 2-bit codes in the low bits of each byte.  (x>>1 ^ x>>2) & 3 maps
@@ -396,10 +402,10 @@ __device__ __forceinline__ void emit_masked(int lane, const uint8_t* s_pos, cons
 // the hot loop's instruction-cache footprint.
 template <int K, int kTile>
 static __device__ __noinline__ void mark_invalid(DevBatch const& b, uint32_t* s_invalid, int lane, int64_t T0,
-                                                 uint32_t c0) {
-    constexpr int kMaskWords = kTile / 32;
+                                                 uint32_t c0, int n_starts = kTile) {
+    const int kMaskWords = (n_starts + 31) / 32;  // (the scan form also asks about the start after the tile)
     const int64_t first = int64_t(b.first_base), end = int64_t(b.end_base);
-    const int64_t tile_end = T0 + kTile;
+    const int64_t tile_end = T0 + n_starts;
     if (T0 < first) {  // head padding of the first tile (< 16 positions)
         int n = int(first - T0);
         if (lane == 0) atomicOr(&s_invalid[0], (1u << n) - 1u);
@@ -499,10 +505,187 @@ static __device__ __noinline__ void slow_tile(DevImage const& f, const uint32_t*
     __syncwarp();
 }
 
+// ---- build-side form: records straight from the tile ----------------------------------------------
+// (minimizer::from_string, include/minimizer.hpp:11-170, as the stateless definition SURVEY.md S2':
+// one record per maximal run of consecutive k-mers of a contig with the same minimizer occurrence)
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr uint64_t kDescValid = uint64_t(1) << 63;
+constexpr int kRecChunk = 256;  // records staged in shared memory at a time
+
+// first start >= x that yields a k-mer (bit clear in s_invalid); the caller guarantees there is one
+// at or before the tile's last start
+__device__ __forceinline__ int next_valid_start(const uint32_t* s_invalid, int x) {
+    int w = x >> 5;
+    uint32_t bits = ~s_invalid[w] & (0xFFFFFFFFu << (x & 31));
+    while (!bits) bits = ~s_invalid[++w];
+    return (w << 5) + __ffs(bits) - 1;
+}
+
+// One tile of the build-side scan after phase B (s_pos: minimizer position of every start).  A record
+// belongs to the tile in which its run ENDS; a run that is still open at the tile's last start is
+// finished by the next tile, which learns where it began from this tile's descriptor.  Record
+// indices come from a decoupled look-back over the per-tile record counts (chained scan: every tile
+// publishes its count at once and the inclusive prefix as soon as its predecessors' are known).
+template <int K, int M>
+__device__ __forceinline__ void scan_tail(DevBatch const& b, TileArgs const& a, uint64_t seed, uint32_t tile,
+                                          int64_t T0, TileRec const& cur, bool tile_clean, int lane,
+                                          const uint8_t* s_pos, const uint32_t* s_invalid, const uint32_t* s_packed,
+                                          unsigned char* scratch) {
+    using C = Cfg<K, M>;
+    constexpr int kTile = C::Tile, W = C::W;
+    constexpr int kRows = (kTile + 31) / 32;  // mask words holding starts 0 .. kTile-1
+    uint16_t* s_ends = reinterpret_cast<uint16_t*>(scratch);              // u16[kSlots]: last start of every run that ends here
+    uint16_t* s_rec = reinterpret_cast<uint16_t*>(scratch + 2 * kSlots);  // kRecChunk records of 9 u16
+    // V: starts that yield a k-mer (lane r holds word r; bit kTile = the start after the tile)
+    const uint32_t inv_w = s_invalid[lane];
+    uint32_t V = ~inv_w;
+    if (lane * 32 > kTile) V = 0;
+    else if (lane * 32 + 31 > kTile) V &= (2u << (kTile - lane * 32)) - 1u;
+    // D: bit q set iff start q+1 has another minimizer than start q (absolute position = s_pos + q & ~15)
+    uint32_t D = 0;
+#pragma unroll 4
+    for (int r = 0; r < kRows; ++r) {
+        const int q = lane + r * 32;
+        const int p0 = int(s_pos[q]) + (q & ~15), p1 = int(s_pos[q + 1]) + ((q + 1) & ~15);
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, p0 != p1);
+        if (lane == r) D = bal;
+    }
+    // does the run of the tile's last start go on into the next tile?  The start after the tile keeps
+    // minimizer P of the last start iff P is still inside its window and the m-mer that enters on the
+    // right is not smaller (strict '<' moves the minimum: include/minimizer.hpp:94)
+    bool cont = false;
+    {
+        const bool both = !((s_invalid[(kTile - 1) >> 5] >> ((kTile - 1) & 31)) & 1u) && !((s_invalid[kTile >> 5] >> (kTile & 31)) & 1u);
+        if (both) {
+            const int P = int(s_pos[kTile - 1]) + ((kTile - 1) & ~15);
+            if (P >= kTile && lane == 0)
+                cont = murmur64(mmer_at<M>(s_packed, kTile + W - 1), seed) >= murmur64(mmer_at<M>(s_packed, P), seed);
+            cont = __shfl_sync(0xFFFFFFFFu, cont ? 1 : 0, 0) != 0;
+        }
+    }
+    if (lane == (kTile - 1) / 32) D = (D & ~(1u << ((kTile - 1) & 31))) | ((cont ? 0u : 1u) << ((kTile - 1) & 31));
+    // E: run ends = valid starts whose successor is invalid or has another minimizer
+    const uint32_t V_up = __shfl_down_sync(0xFFFFFFFFu, V, 1);            // word r+1
+    const uint32_t Vnext = (V >> 1) | ((lane < 31 ? V_up : 0u) << 31);     // bit q = V(q + 1)
+    uint32_t E = V & (~Vnext | D);
+    if (lane * 32 >= kTile) E = 0;
+    else if (lane * 32 + 32 > kTile) E &= (1u << (kTile - lane * 32)) - 1u;
+    const uint32_t n_mine = __popc(E);
+    uint32_t inc = n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const uint32_t count = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    {
+        uint16_t* lp = s_ends + (inc - n_mine);
+        uint32_t word = E;
+        while (word) {  // ascending: the list is in scan order
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            *lp++ = uint16_t(lane * 32 + bit);
+        }
+    }
+    __syncwarp();
+    // descriptor: [63] valid, [28] a run is open at the tile's end, [16..27] where it began, [0..15] count
+    uint32_t carry_out = 0;
+    if (cont) carry_out = uint32_t(next_valid_start(s_invalid, count ? int(s_ends[count - 1]) + 1 : 0));
+    uint64_t* descA = a.desc + 2 * uint64_t(tile);
+    if (lane == 0) st_release_u64(descA, kDescValid | (uint64_t(cont ? 1 : 0) << 28) | (uint64_t(carry_out) << 16) | count);
+    // look back: exclusive prefix of the counts; the predecessor also says whether its last run is open
+    uint64_t excl = 0;
+    bool open_in = false;
+    int carry_in = 0;
+    if (tile > 0) {
+        int64_t j0 = int64_t(tile) - 1;
+        bool first_window = true;
+        for (;;) {
+            const int64_t j = j0 - lane;
+            uint64_t av = 0, pv = 0;
+            if (j >= 0) {
+                do av = ld_acquire_u64(a.desc + 2 * j); while (!(av & kDescValid));
+                pv = ld_acquire_u64(a.desc + 2 * j + 1);
+            }
+            if (first_window) {
+                const uint64_t a1 = __shfl_sync(0xFFFFFFFFu, av, 0);
+                open_in = (a1 >> 28) & 1u;
+                carry_in = int((a1 >> 16) & 0xFFFu);
+                first_window = false;
+            }
+            const uint32_t have_p = __ballot_sync(0xFFFFFFFFu, j >= 0 && (pv & kDescValid));
+            const int stop = have_p ? __ffs(have_p) - 1 : 32;  // nearest predecessor whose inclusive prefix is known
+            uint64_t contrib = 0;
+            if (j >= 0 && lane < stop) contrib = av & 0xFFFFu;
+            else if (lane == stop) contrib = pv & ~kDescValid;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
+            excl += contrib;
+            if (have_p || j0 < 32) break;
+            j0 -= 32;
+        }
+    }
+    if (lane == 0) {
+        st_release_u64(descA + 1, kDescValid | (excl + count));
+        if (tile + 1 == a.n_tiles) *a.n_records = excl + count;
+    }
+    if (count == 0) return;
+    // contig of the tile (a clean tile lies inside one contig; otherwise every record looks its own up)
+    uint64_t c_start = 0, c_idb = 0;
+    if (tile_clean) {
+        c_start = __ldg(b.offsets + cur.c0);
+        c_idb = __ldg(a.id_base + cur.c0);
+    }
+    const bool v0 = !(s_invalid[0] & 1u);
+#pragma unroll 1
+    for (uint32_t e0 = 0; e0 < count; e0 += kRecChunk) {
+        const uint32_t e1 = e0 + kRecChunk < count ? e0 + kRecChunk : count;
+#pragma unroll 1
+        for (uint32_t e = e0 + lane; e < e1; e += 32) {
+            const int q_e = s_ends[e];
+            int q_s;  // tile-local start of the run's first k-mer (negative: it began in the previous tile)
+            if (e == 0) q_s = v0 ? (open_in ? carry_in - kTile : 0) : next_valid_start(s_invalid, 0);
+            else q_s = next_valid_start(s_invalid, int(s_ends[e - 1]) + 1);
+            const int P = int(s_pos[q_e]) + (q_e & ~15);
+            const uint64_t mm = mmer_at<M>(s_packed, P);
+            uint64_t cs = c_start, idb = c_idb;
+            if (!tile_clean) {
+                const uint64_t at = uint64_t(T0 + q_e);
+                uint64_t lo = cur.c0, hi = b.n_contigs;  // offsets[lo] <= at < offsets[hi]
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (__ldg(b.offsets + mid) <= at) lo = mid; else hi = mid;
+                }
+                cs = __ldg(b.offsets + lo);
+                idb = __ldg(a.id_base + lo);
+            }
+            const uint64_t id = idb + (uint64_t(T0 + P) - cs);
+            uint16_t* q = s_rec + (e - e0) * 9;  // 18-byte packed mm_record_t (include/constants.hpp:26-33)
+            q[0] = uint16_t(mm); q[1] = uint16_t(mm >> 16); q[2] = uint16_t(mm >> 32); q[3] = uint16_t(mm >> 48);
+            q[4] = uint16_t(id); q[5] = uint16_t(id >> 16); q[6] = uint16_t(id >> 32); q[7] = uint16_t(id >> 48);
+            q[8] = uint16_t(uint32_t(P - q_s) | (uint32_t(q_e - q_s + 1) << 8));  // p1, size
+            a.start_pos[excl + e] = uint32_t(uint64_t(T0 + q_s) - b.first_base);
+        }
+        __syncwarp();
+        uint16_t* dst = reinterpret_cast<uint16_t*>(a.records) + (excl + e0) * 9;  // records are 2-byte aligned
+        const uint32_t n16 = (e1 - e0) * 9;
+        for (uint32_t t = lane; t < n16; t += 32) dst[t] = s_rec[t];
+        __syncwarp();
+    }
+}
+
 // kScan = true: the build-side form (minimizer::from_string, include/minimizer.hpp:11-170).  Phases A
-// and B only; instead of hash codes the kernel writes, per valid k-mer start and in the same dense
-// order, the offset of its minimizer inside the k-mer (one byte, b.codes reinterpreted), from which
-// the super-k-mer heads follow (scan_kernels.cu).  `f` then only carries k, m and the seed.
+// and B, then scan_tail: the packed 18-byte records of the super-k-mers that end in the tile, written in
+// scan order at the index a chained scan over the tiles assigns (no per-k-mer array ever reaches
+// global memory).  `f` then only carries k, m and the seed; the grid is one warp per tile (not
+// persistent), so that tiles start in index order and the look-back stays short.
 template <int K, int M, bool kScan = false>
 __global__ void __launch_bounds__(kThreads, (Cfg<K, M>::E == 1 ? LPHB_MINB : LPHB_MINB_WIDE))
 k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBatch b,
@@ -607,7 +790,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         // k-mer starts that produce no code (contig seams, short contigs, positions outside
         // [first, end)) -> s_invalid; nothing to do when one contig covers the tile and k-1 more bases
         const bool tile_clean = cur.clean != 0;
-        if (!tile_clean) mark_invalid<K, kTile>(b, s_invalid, lane, T0, cur.c0);
+        if (!tile_clean) mark_invalid<K, kTile>(b, s_invalid, lane, T0, cur.c0, kScan ? kTile + 1 : kTile);
         // exclusive prefix of invalid counts per mask word (one word per lane)
         bool tile_has_invalid = false;
         {
@@ -753,19 +936,8 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
         __syncwarp();
 
         if constexpr (kScan) {
-            // position-parallel: minimizer offset of every valid k-mer start, dense order
-            uint8_t* outp = reinterpret_cast<uint8_t*>(b.codes) + cur.out;
-            const uint32_t lt = (1u << lane) - 1u;
-            const int lane16 = lane & 16;
-#pragma unroll 4
-            for (int r = 0; r < kTile / 32; ++r) {
-                const int q = lane + r * 32;
-                const uint32_t mw = tile_has_invalid ? s_invalid[r] : 0u;  // uniform in the warp
-                if ((mw >> lane) & 1u) continue;
-                // s_pos holds the position relative to the owning thread's first start (q & ~15)
-                const int p = int(s_pos[q]) + lane16 + r * 32 - q;
-                outp[q - int(s_invpre[r]) - __popc(mw & lt)] = uint8_t(p);
-            }
+            scan_tail<K, M>(b, a, f.mm_seed, tile, T0, cur, tile_clean, lane, s_pos, s_invalid, s_packed,
+                            reinterpret_cast<unsigned char*>(s_ent));
             __syncwarp();
             continue;
         }
@@ -905,7 +1077,7 @@ k_query_tiled(const __grid_constant__ DevImage f, const __grid_constant__ DevBat
 // per tile: contig containing its first in-range position, number of valid k-mer starts before it,
 // and whether one contig covers the tile plus k-1 bases (then every start yields a code)
 __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, uint32_t n_tiles,
-                             uint32_t k, int kTile, TileRec* recs) {
+                             uint32_t k, int kTile, int extra, TileRec* recs) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const int64_t t0 = pos0 + int64_t(t) * kTile;
@@ -922,7 +1094,7 @@ __global__ void k_tile_setup(const __grid_constant__ DevBatch b, int64_t pos0, u
     TileRec r;
     r.c0 = uint32_t(lo);
     r.out = __ldg(b.code_off + lo) + (before < cnt ? before : cnt);
-    r.clean = (t0 >= int64_t(b.first_base) && int64_t(s) <= t0 && int64_t(e) >= t0 + kTile + int64_t(k) - 1) ? 1u : 0u;
+    r.clean = (t0 >= int64_t(b.first_base) && int64_t(s) <= t0 && int64_t(e) >= t0 + kTile + extra + int64_t(k) - 1) ? 1u : 0u;
     recs[t] = r;
 }
 
@@ -951,7 +1123,8 @@ void launch_cfg(DevImage const& img, DevBatch const& b, TileArgs const& a, cudaS
     const int resident = resident_ctas<K, M, kScan>();
     // persistent grid: every warp walks tiles (global warp id) + i * (number of warps)
     const uint32_t ctas_needed = (a.n_tiles + kWarps - 1) / kWarps;
-    const uint32_t grid = ctas_needed < uint32_t(resident) ? ctas_needed : uint32_t(resident);
+    // (the scan form is not persistent: tiles must start in index order for its chained scan)
+    const uint32_t grid = (kScan || ctas_needed < uint32_t(resident)) ? ctas_needed : uint32_t(resident);
     k_query_tiled<K, M, kScan><<<grid, kThreads, kSmemBytes, stream>>>(img, b, a);
 }
 
@@ -972,10 +1145,17 @@ bool pick_cfg(uint32_t k, uint32_t m, bool scan, LaunchFn& fn, int& tile) {
     return fn != nullptr;
 }
 
-bool launch_tiled(DevImage const& img, DevBatch const& b, bool scan, cudaStream_t stream) {
+struct ScanOut {
+    uint8_t* records;
+    uint32_t* start_pos;
+    const uint64_t* id_base;
+    unsigned long long* n_records;
+};
+
+bool launch_tiled(DevImage const& img, DevBatch const& b, const ScanOut* scan, cudaStream_t stream) {
     LaunchFn fn;
     int tile = 0;  // k-mer starts per tile of the instantiation
-    if (!pick_cfg(img.k, img.m, scan, fn, tile)) return false;
+    if (!pick_cfg(img.k, img.m, scan != nullptr, fn, tile)) return false;
     if (!b.tile_ws || b.n_contigs == 0 || b.n_contigs >= (1ull << 32)) return false;
     if (b.end_base <= b.first_base) return true;
     TileArgs a{};
@@ -990,7 +1170,15 @@ bool launch_tiled(DevImage const& img, DevBatch const& b, bool scan, cudaStream_
     if (query_tiled_ws_bytes(b.end_base - b.first_base) > b.tile_ws_bytes) return false;
     TileRec* recs = reinterpret_cast<TileRec*>(b.tile_ws);
     a.recs = recs;
-    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, img.k, tile, recs);
+    if (scan) {
+        a.records = scan->records;
+        a.start_pos = scan->start_pos;
+        a.id_base = scan->id_base;
+        a.n_records = scan->n_records;
+        a.desc = reinterpret_cast<uint64_t*>(recs + n_tiles);  // second half of the workspace
+        cudaMemsetAsync(a.desc, 0, n_tiles * 16, stream);
+    }
+    k_tile_setup<<<(a.n_tiles + 255) / 256, 256, 0, stream>>>(b, a.pos0, a.n_tiles, img.k, tile, scan ? 1 : 0, recs);
     fn(img, b, a, stream);
     return true;
 }
@@ -999,20 +1187,29 @@ bool launch_tiled(DevImage const& img, DevBatch const& b, bool scan, cudaStream_
 
 uint64_t query_tiled_ws_bytes(uint64_t span_bases) {
     uint64_t n_tiles = (span_bases + 16) / kMinTile + 2;
-    return n_tiles * sizeof(TileRec) + 64;
+    return n_tiles * (sizeof(TileRec) + 16) + 64;  // per tile: its set-up record + (scan form) its chained-scan descriptor
 }
 
 bool launch_query_tiled(DevImage const& img, DevBatch const& b, cudaStream_t stream) {
-    return launch_tiled(img, b, false, stream);
+    return launch_tiled(img, b, nullptr, stream);
 }
 
-bool launch_scan_pos_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, cudaStream_t stream) {
+bool launch_scan_records_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch const& b, const uint64_t* d_id_base,
+                               uint8_t* d_records, uint32_t* d_start_pos, unsigned long long* d_n_records,
+                               cudaStream_t stream) {
     DevImage img{};  // the scan form reads k, m and the minimizer seed only
     img.k = k;
     img.m = m;
     img.w = k - m + 1;
     img.mm_seed = seed;
-    return launch_tiled(img, b, true, stream);
+    ScanOut out{d_records, d_start_pos, d_id_base, d_n_records};
+    return launch_tiled(img, b, &out, stream);
+}
+
+bool scan_tiled_available(uint32_t k, uint32_t m) {
+    LaunchFn fn;
+    int tile = 0;
+    return pick_cfg(k, m, true, fn, tile);
 }
 
 }  // namespace lphb

@@ -173,7 +173,7 @@ constexpr int kEmitChunk = 1024;
 __global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanBatch b,
                                                    const uint8_t* head, const uint8_t* pos,
                                                    const uint32_t* rank, uint8_t* records,
-                                                   uint32_t* head_at) {
+                                                   uint32_t* start_pos) {
     __shared__ __align__(16) uint16_t s_rec[kEmitChunk * 9];
     __shared__ uint16_t s_list[kEmitChunk];
     __shared__ uint64_t s_c0;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_scan_emit(const __grid_constant__ ScanB
             q[0] = uint16_t(mm); q[1] = uint16_t(mm >> 16); q[2] = uint16_t(mm >> 32); q[3] = uint16_t(mm >> 48);
             q[4] = uint16_t(id); q[5] = uint16_t(id >> 16); q[6] = uint16_t(id >> 32); q[7] = uint16_t(id >> 48);
             q[8] = uint16_t(p1 | (uint32_t(e - d) << 8));
-            head_at[r0 + t] = uint32_t(d);
+            start_pos[r0 + t] = uint32_t(i - b.first_base);
         }
         __syncthreads();
         uint16_t* dst = reinterpret_cast<uint16_t*>(records) + uint64_t(r0) * 9;  // records are 2-byte aligned
@@ -246,35 +246,36 @@ __global__ void k_colliding_mark(const uint8_t* records, uint64_t n_records, con
     }
 }
 
-__global__ void __launch_bounds__(256) k_colliding_emit(const __grid_constant__ ScanBatch b,
-                                                        const uint32_t* rank,
-                                                        const uint32_t* head_at,
-                                                        const uint32_t* take,
-                                                        const uint64_t* out_off, int kmer_bits,
-                                                        uint8_t* kmers) {
+// get_colliding_kmers: the forward k-mers of every taken record, in scan order.  One thread per record
+// (about 1 % of them are taken; a record has at most k - m + 1 k-mers).
+__global__ void __launch_bounds__(256) k_colliding_emit(const __grid_constant__ ScanBatch b, uint64_t n_records,
+                                                        const uint32_t* start_pos, const uint32_t* take,
+                                                        const uint64_t* out_off, int kmer_bits, uint8_t* kmers) {
     const uint32_t k = b.k;
-    uint64_t span = b.end_base - b.first_base;
-    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < span;
-         t += uint64_t(gridDim.x) * blockDim.x) {
-        uint64_t i = b.first_base + t;
-        uint64_t c = find_contig(b.offsets, b.n_contigs, i);
-        uint64_t start = __ldg(b.offsets + c), end = __ldg(b.offsets + c + 1);
-        if (i + k > end || b.dirty[c]) continue;
-        uint64_t d = __ldg(b.code_off + c) + (i - start);
-        uint32_t r = rank[d + 1] - 1;  // record containing k-mer d (heads before or at d, minus 1)
-        if (!take[r]) continue;
+    const uint64_t lo_mask = k >= 32 ? ~uint64_t(0) : ((uint64_t(1) << (2 * k)) - 1);
+    const uint64_t hi_mask = k > 32 ? ((uint64_t(1) << (2 * k - 64)) - 1) : 0;
+    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < n_records;
+         r += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t n = take[r];
+        if (!n) continue;
+        const char* s = b.bases + b.first_base + start_pos[r];
         uint64_t lo = 0, hi = 0;
-        for (uint32_t j = 0; j < k; ++j) {
-            uint32_t code = nt4(uint8_t(b.bases[i + j]));
+        for (uint32_t j = 0; j + 1 < k; ++j) {  // first k - 1 bases
+            const uint32_t code = nt4(uint8_t(s[j])) & 3u;
             hi = (hi << 2) | (lo >> 62);
-            lo = (lo << 2) | (code & 3);
+            lo = (lo << 2) | code;
         }
-        uint64_t o = out_off[r] + (d - head_at[r]);
-        if (kmer_bits == 64) {
-            reinterpret_cast<uint64_t*>(kmers)[o] = lo;
-        } else {
-            reinterpret_cast<uint64_t*>(kmers)[2 * o] = lo;
-            reinterpret_cast<uint64_t*>(kmers)[2 * o + 1] = hi;
+        uint64_t o = out_off[r];
+        for (uint32_t j = 0; j < n; ++j, ++o) {
+            const uint32_t code = nt4(uint8_t(s[k - 1 + j])) & 3u;
+            hi = ((hi << 2) | (lo >> 62)) & hi_mask;
+            lo = ((lo << 2) | code) & lo_mask;
+            if (kmer_bits == 64) {
+                reinterpret_cast<uint64_t*>(kmers)[o] = lo;
+            } else {
+                reinterpret_cast<uint64_t*>(kmers)[2 * o] = lo;
+                reinterpret_cast<uint64_t*>(kmers)[2 * o + 1] = hi;
+            }
         }
     }
 }
@@ -336,9 +337,9 @@ void launch_head_ranks(const uint8_t* head, uint64_t n_kmers, uint32_t* rank, vo
 }
 
 void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
-                      const uint32_t* rank, uint8_t* records, uint32_t* head_at, cudaStream_t stream) {
+                      const uint32_t* rank, uint8_t* records, uint32_t* start_pos, cudaStream_t stream) {
     if (!b.n_kmers) return;
-    k_scan_emit<<<grid_for((b.n_kmers + 3) / 4), 256, 0, stream>>>(b, head, pos, rank, records, head_at);
+    k_scan_emit<<<grid_for((b.n_kmers + 3) / 4), 256, 0, stream>>>(b, head, pos, rank, records, start_pos);
 }
 
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
@@ -376,12 +377,11 @@ void launch_exclusive_u32(const uint32_t* in, uint64_t n, uint64_t* out, void* d
     k_finish_u32<<<1, 1, 0, stream>>>(in, n, out);
 }
 
-void launch_colliding_emit(ScanBatch const& b, const uint32_t* rank, const uint32_t* head_at,
+void launch_colliding_emit(ScanBatch const& b, uint64_t n_records, const uint32_t* start_pos,
                            const uint32_t* take, const uint64_t* out_off, int kmer_bits,
                            uint8_t* kmers, cudaStream_t stream) {
-    uint64_t span = b.end_base - b.first_base;
-    if (!span) return;
-    k_colliding_emit<<<grid_for(span), 256, 0, stream>>>(b, rank, head_at, take, out_off, kmer_bits, kmers);
+    if (!n_records) return;
+    k_colliding_emit<<<grid_for(n_records), 256, 0, stream>>>(b, n_records, start_pos, take, out_off, kmer_bits, kmers);
 }
 
 }  // namespace lphb

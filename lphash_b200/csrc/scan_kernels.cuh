@@ -33,9 +33,10 @@ void launch_head_ranks(const uint8_t* head, uint64_t n_kmers, uint32_t* rank, vo
                        uint64_t tmp_bytes, cudaStream_t stream);
 uint64_t head_ranks_tmp_bytes(uint64_t n_kmers);
 
-// Pass 2: write the 18-byte records {itself, id, p1, size} and head_at[r] = dense index of record r.
+// Pass 2: write the 18-byte records {itself, id, p1, size} and start_pos[r] = stream position of
+// record r's first k-mer, relative to b.first_base.
 void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
-                      const uint32_t* rank, uint8_t* records, uint32_t* head_at, cudaStream_t stream);
+                      const uint32_t* rank, uint8_t* records, uint32_t* start_pos, cudaStream_t stream);
 
 // get_colliding_kmers: take[r] = (record r's id is in ids) ? size : 0 ...
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
@@ -44,7 +45,7 @@ void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uin
 void launch_exclusive_u32(const uint32_t* in, uint64_t n, uint64_t* out, void* d_tmp,
                           uint64_t tmp_bytes, cudaStream_t stream);
 uint64_t exclusive_u32_tmp_bytes(uint64_t n);
-void launch_colliding_emit(ScanBatch const& b, const uint32_t* rank, const uint32_t* head_at,
+void launch_colliding_emit(ScanBatch const& b, uint64_t n_records, const uint32_t* start_pos,
                            const uint32_t* take, const uint64_t* out_off, int kmer_bits,
                            uint8_t* kmers, cudaStream_t stream);
 
