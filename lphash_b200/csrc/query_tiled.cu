@@ -508,13 +508,15 @@ static __device__ __noinline__ void slow_tile(DevImage const& f, const uint32_t*
 // ---- build-side form: records straight from the tile ----------------------------------------------
 // (minimizer::from_string, include/minimizer.hpp:11-170, as the stateless definition SURVEY.md S2':
 // one record per maximal run of consecutive k-mers of a contig with the same minimizer occurrence)
-__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+// descriptor words are self-contained 64-bit values (nothing else is read on their authority), so
+// relaxed device-scope accesses are enough: no fence on either side
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) {
     uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_desc(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 constexpr uint64_t kDescValid = uint64_t(1) << 63;
 constexpr int kRecChunk = 256;  // records staged in shared memory at a time
@@ -599,44 +601,7 @@ __device__ __forceinline__ void scan_tail(DevBatch const& b, TileArgs const& a, 
     uint32_t carry_out = 0;
     if (cont) carry_out = uint32_t(next_valid_start(s_invalid, count ? int(s_ends[count - 1]) + 1 : 0));
     uint64_t* descA = a.desc + 2 * uint64_t(tile);
-    if (lane == 0) st_release_u64(descA, kDescValid | (uint64_t(cont ? 1 : 0) << 28) | (uint64_t(carry_out) << 16) | count);
-    // look back: exclusive prefix of the counts; the predecessor also says whether its last run is open
-    uint64_t excl = 0;
-    bool open_in = false;
-    int carry_in = 0;
-    if (tile > 0) {
-        int64_t j0 = int64_t(tile) - 1;
-        bool first_window = true;
-        for (;;) {
-            const int64_t j = j0 - lane;
-            uint64_t av = 0, pv = 0;
-            if (j >= 0) {
-                do av = ld_acquire_u64(a.desc + 2 * j); while (!(av & kDescValid));
-                pv = ld_acquire_u64(a.desc + 2 * j + 1);
-            }
-            if (first_window) {
-                const uint64_t a1 = __shfl_sync(0xFFFFFFFFu, av, 0);
-                open_in = (a1 >> 28) & 1u;
-                carry_in = int((a1 >> 16) & 0xFFFu);
-                first_window = false;
-            }
-            const uint32_t have_p = __ballot_sync(0xFFFFFFFFu, j >= 0 && (pv & kDescValid));
-            const int stop = have_p ? __ffs(have_p) - 1 : 32;  // nearest predecessor whose inclusive prefix is known
-            uint64_t contrib = 0;
-            if (j >= 0 && lane < stop) contrib = av & 0xFFFFu;
-            else if (lane == stop) contrib = pv & ~kDescValid;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
-            excl += contrib;
-            if (have_p || j0 < 32) break;
-            j0 -= 32;
-        }
-    }
-    if (lane == 0) {
-        st_release_u64(descA + 1, kDescValid | (excl + count));
-        if (tile + 1 == a.n_tiles) *a.n_records = excl + count;
-    }
-    if (count == 0) return;
+    if (lane == 0) st_desc(descA, kDescValid | (uint64_t(cont ? 1 : 0) << 28) | (uint64_t(carry_out) << 16) | count);
     // contig of the tile (a clean tile lies inside one contig; otherwise every record looks its own up)
     uint64_t c_start = 0, c_idb = 0;
     if (tile_clean) {
@@ -644,14 +609,21 @@ __device__ __forceinline__ void scan_tail(DevBatch const& b, TileArgs const& a, 
         c_idb = __ldg(a.id_base + cur.c0);
     }
     const bool v0 = !(s_invalid[0] & 1u);
+    int16_t* s_qs = reinterpret_cast<int16_t*>(s_rec + kRecChunk * 9);  // per staged record: its first start (tile-local)
+    uint64_t excl = 0;
+    bool open_in = false, looked = false;
+    int carry_in = 0;
+    // The look-back waits for the predecessors, so everything that does not need its result goes
+    // first: the records of a chunk are built in shared memory (the first one provisionally: whether it
+    // began in the previous tile is the predecessor's news), then the prefix is fetched, then they leave.
 #pragma unroll 1
-    for (uint32_t e0 = 0; e0 < count; e0 += kRecChunk) {
+    for (uint32_t e0 = 0; e0 < count || !looked; e0 += kRecChunk) {
         const uint32_t e1 = e0 + kRecChunk < count ? e0 + kRecChunk : count;
 #pragma unroll 1
         for (uint32_t e = e0 + lane; e < e1; e += 32) {
             const int q_e = s_ends[e];
-            int q_s;  // tile-local start of the run's first k-mer (negative: it began in the previous tile)
-            if (e == 0) q_s = v0 ? (open_in ? carry_in - kTile : 0) : next_valid_start(s_invalid, 0);
+            int q_s;  // tile-local start of the run's first k-mer
+            if (e == 0) q_s = v0 ? 0 : next_valid_start(s_invalid, 0);
             else q_s = next_valid_start(s_invalid, int(s_ends[e - 1]) + 1);
             const int P = int(s_pos[q_e]) + (q_e & ~15);
             const uint64_t mm = mmer_at<M>(s_packed, P);
@@ -671,12 +643,59 @@ __device__ __forceinline__ void scan_tail(DevBatch const& b, TileArgs const& a, 
             q[0] = uint16_t(mm); q[1] = uint16_t(mm >> 16); q[2] = uint16_t(mm >> 32); q[3] = uint16_t(mm >> 48);
             q[4] = uint16_t(id); q[5] = uint16_t(id >> 16); q[6] = uint16_t(id >> 32); q[7] = uint16_t(id >> 48);
             q[8] = uint16_t(uint32_t(P - q_s) | (uint32_t(q_e - q_s + 1) << 8));  // p1, size
-            a.start_pos[excl + e] = uint32_t(uint64_t(T0 + q_s) - b.first_base);
+            s_qs[e - e0] = int16_t(q_s);
+        }
+        if (!looked) {
+            looked = true;
+            // look back: exclusive prefix of the counts; the predecessor also says whether its last run is open
+            if (tile > 0) {
+                int64_t j0 = int64_t(tile) - 1;
+                bool first_window = true;
+                for (;;) {
+                    const int64_t j = j0 - lane;
+                    uint64_t av = 0, pv = 0;
+                    if (j >= 0) {
+                        do av = ld_desc(a.desc + 2 * j); while (!(av & kDescValid));
+                        pv = ld_desc(a.desc + 2 * j + 1);
+                    }
+                    if (first_window) {
+                        const uint64_t a1 = __shfl_sync(0xFFFFFFFFu, av, 0);
+                        open_in = (a1 >> 28) & 1u;
+                        carry_in = int((a1 >> 16) & 0xFFFu);
+                        first_window = false;
+                    }
+                    const uint32_t have_p = __ballot_sync(0xFFFFFFFFu, j >= 0 && (pv & kDescValid));
+                    const int stop = have_p ? __ffs(have_p) - 1 : 32;  // nearest predecessor whose inclusive prefix is known
+                    uint64_t contrib = 0;
+                    if (j >= 0 && lane < stop) contrib = av & 0xFFFFu;
+                    else if (lane == stop) contrib = pv & ~kDescValid;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
+                    excl += contrib;
+                    if (have_p || j0 < 32) break;
+                    j0 -= 32;
+                }
+            }
+            if (lane == 0) {
+                st_desc(descA + 1, kDescValid | (excl + count));
+                if (tile + 1 == a.n_tiles) *a.n_records = excl + count;
+            }
+            __syncwarp();
+            if (count && v0 && open_in && lane == 0) {  // the first run began in the previous tile
+                const int q_s = carry_in - kTile, q_e = s_ends[0];
+                const int P = int(s_pos[q_e]) + (q_e & ~15);
+                s_rec[8] = uint16_t(uint32_t(P - q_s) | (uint32_t(q_e - q_s + 1) << 8));
+                s_qs[0] = int16_t(q_s);
+            }
         }
         __syncwarp();
-        uint16_t* dst = reinterpret_cast<uint16_t*>(a.records) + (excl + e0) * 9;  // records are 2-byte aligned
-        const uint32_t n16 = (e1 - e0) * 9;
-        for (uint32_t t = lane; t < n16; t += 32) dst[t] = s_rec[t];
+        if (e1 > e0) {
+            for (uint32_t e = e0 + lane; e < e1; e += 32)
+                a.start_pos[excl + e] = uint32_t(uint64_t(T0 + int(s_qs[e - e0])) - b.first_base);
+            uint16_t* dst = reinterpret_cast<uint16_t*>(a.records) + (excl + e0) * 9;  // records are 2-byte aligned
+            const uint32_t n16 = (e1 - e0) * 9;
+            for (uint32_t t = lane; t < n16; t += 32) dst[t] = s_rec[t];
+        }
         __syncwarp();
     }
 }
