@@ -67,6 +67,7 @@ struct DevBuf {
 struct Workspace {
     DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
     DevBuf r_start, r_head, r_rank, r_head_at, r_tmp, r_runs, r_count;  // run-length form of the codes (lphb_query_stream_runs)
+    DevBuf q_bases, q_flag, q_voff, q_vstart, q_status, q_tmp, q_vcode_off, q_dirty, q_tile, q_spur, q_spur_cnt, q_out_off, q_out;  // non-ACGT contigs
     unsigned long long* h_counts = nullptr;  // pinned: runs per chunk
     uint64_t h_counts_cap = 0;
     std::vector<cudaEvent_t> ev_cnt;         // per chunk: its run count has reached h_counts
@@ -113,7 +114,9 @@ struct Workspace {
     }
     void destroy() {
         for (DevBuf* b : {&bases, &offsets, &code_off, &codes, &dirty, &status, &tmp, &aux0, &aux1,
-                          &aux2, &aux3, &codes2, &tile, &r_start, &r_head, &r_rank, &r_head_at, &r_tmp, &r_runs, &r_count})
+                          &aux2, &aux3, &codes2, &tile, &r_start, &r_head, &r_rank, &r_head_at, &r_tmp, &r_runs, &r_count,
+                          &q_bases, &q_flag, &q_voff, &q_vstart, &q_status, &q_tmp, &q_vcode_off, &q_dirty, &q_tile, &q_spur,
+                          &q_spur_cnt, &q_out_off, &q_out})
             b->release();
         if (h_counts) cudaFreeHost(h_counts);
         for (cudaEvent_t e : ev_cnt) cudaEventDestroy(e);
@@ -473,6 +476,20 @@ int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* 
 
 namespace {
 
+// LPHB_SCAN_TRACE=1: per-stage wall times of the scan on stderr (each mark synchronizes the stream)
+struct ScanTrace {
+    bool on;
+    explicit ScanTrace(const char* env = "LPHB_SCAN_TRACE") : on(getenv(env) != nullptr) {}
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(cudaStream_t s, const char* what) {
+        if (!on) return;
+        if (s) cudaStreamSynchronize(s);
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lphb scan] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 // What the caller wants back: the codes themselves (8 B per k-mer) or their run-length form (12-byte
 // records, about 2 B per k-mer: runs_kernels.cu).
 struct RunSink {
@@ -685,31 +702,91 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
             f->stats.d2h_bytes = total * 8 + 32;
             return LPHB_OK;
         }
-        // ---- contigs with non-ACGT bytes: exact sequential emulation ----------
+        // ---- contigs with non-ACGT bytes (quirk_kernels.cu) --------------------------------
+        // Their valid k-mers are ordinary work: the contigs are gathered into a compact batch, cut into
+        // maximal runs of valid / invalid bytes, and the runs go through the same query kernel as contigs
+        // of their own.  Only the reference's spurious codes (pushed while a run is shorter than k) need the
+        // sequential state machine, one thread per episode of a few dozen bases.
+        ScanTrace qtr("LPHB_QUIRK_TRACE");
+        qtr.mark(s, "clean pass + optimistic copies");
         std::vector<uint8_t> dirty(n_contigs);
         CK(cudaMemcpy(dirty.data(), ws.dirty.p, n_contigs, cudaMemcpyDeviceToHost));
-        std::vector<uint64_t> list, q_off;
-        uint64_t q_total = 0;
+        std::vector<uint64_t> list, q_start;
+        uint64_t q_bytes = 0;
         for (uint64_t c = 0; c < n_contigs; ++c)
             if (dirty[c]) {
-                uint64_t len = offsets[c + 1] - offsets[c];
                 list.push_back(c);
-                q_off.push_back(q_total);
-                q_total += len >= m ? len - m + 1 : 0;  // at most one code per m-mer
+                q_start.push_back(q_bytes);
+                q_bytes += offsets[c + 1] - offsets[c];
             }
-        ws.aux0.reserve(list.size() * 8);
-        ws.aux1.reserve(list.size() * 8);
-        ws.aux2.reserve(list.size() * 8);
-        ws.codes2.reserve(q_total * 8 + 64);
-        CK(cudaMemcpyAsync(ws.aux0.p, list.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ws.aux1.p, q_off.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
-        launch_query_quirk(f->img, b.bases, b.offsets, ws.aux0.as<uint64_t>(), list.size(),
-                           ws.aux1.as<uint64_t>(), ws.codes2.as<uint64_t>(), ws.aux2.as<uint64_t>(), s);
-        f->stats.kernel_launches += 1;
-        std::vector<uint64_t> counts(list.size());
-        CK(cudaMemcpyAsync(counts.data(), ws.aux2.p, list.size() * 8, cudaMemcpyDeviceToHost, s));
+        q_start.push_back(q_bytes);
+        const uint64_t n_list = list.size();
+        const uint32_t w_cap = f->img.w;
+        ws.aux0.reserve(n_list * 8);
+        ws.aux1.reserve((n_list + 1) * 8);
+        ws.aux2.reserve(n_list * 8);
+        ws.q_bases.reserve(q_bytes + 64);
+        ws.q_flag.reserve(q_bytes + 8);
+        ws.q_voff.reserve((q_bytes + 2) * 8);
+        ws.q_vstart.reserve((n_list + 2) * 4);
+        ws.q_status.reserve(64);
+        ws.q_tmp.reserve(std::max<uint64_t>(quirk_tmp_bytes(q_bytes + 1), code_offsets_tmp_bytes(q_bytes + 1)));
+        CK(cudaMemcpyAsync(ws.aux0.p, list.data(), n_list * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ws.aux1.p, q_start.data(), (n_list + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ws.q_bases.as<char>() + q_bytes, 'A', 64, s));  // read-ahead of the last tile
+        launch_gather_contigs(b.bases, b.offsets, ws.aux0.as<uint64_t>(), ws.aux1.as<uint64_t>(), n_list, q_bytes,
+                              ws.q_bases.as<char>(), s);
+        auto* qst = ws.q_status.as<unsigned long long>();
+        launch_find_runs(ws.q_bases.as<char>(), q_bytes, ws.aux1.as<uint64_t>(), n_list, ws.q_flag.as<uint8_t>(),
+                         ws.q_voff.as<uint64_t>(), qst + 4, ws.q_vstart.as<uint32_t>(), ws.q_tmp.p, ws.q_tmp.cap, s);
+        unsigned long long n_v = 0;
+        CK(cudaMemcpyAsync(&n_v, qst + 4, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
+        f->stats.kernel_launches += 7;
+        qtr.mark(s, "gather + find runs");
+        // the runs as a batch of their own: valid k-mers of every run, clean layout per run
+        ws.q_vcode_off.reserve((n_v + 2) * 8);
+        ws.q_dirty.reserve(n_v + 8);
+        ws.codes2.reserve(q_bytes * 8 + 64);
+        ws.q_tile.reserve(query_tiled_ws_bytes(q_bytes));
+        CK(cudaMemsetAsync(ws.q_dirty.p, 0, n_v + 8, s));
+        launch_code_offsets(ws.q_voff.as<uint64_t>(), n_v, k, ws.q_vcode_off.as<uint64_t>(), qst, ws.q_tmp.p, ws.q_tmp.cap, s);
+        {
+            DevBatch bq{};
+            bq.bases = ws.q_bases.as<char>();
+            bq.offsets = ws.q_voff.as<uint64_t>();
+            bq.code_off = ws.q_vcode_off.as<uint64_t>();
+            bq.n_contigs = n_v;
+            bq.first_base = 0;
+            bq.end_base = q_bytes;
+            bq.codes = ws.codes2.as<uint64_t>();
+            bq.dirty = ws.q_dirty.as<uint8_t>();
+            bq.status = qst;
+            bq.tile_ws = ws.q_tile.p;
+            bq.tile_ws_bytes = ws.q_tile.cap;
+            if (!launch_query_tiled(f->img, bq, s)) launch_query_generic(f->img, bq, s);
+            f->stats.kernel_launches += 3;
+        }
+        qtr.mark(s, "runs through the query kernel");
+        ws.q_spur.reserve((n_v + 1) * uint64_t(w_cap) * 8);
+        ws.q_spur_cnt.reserve((n_v + 2) * 4);
+        ws.q_out_off.reserve((n_v + 2) * 8);
+        ws.q_out.reserve((q_bytes + n_v * uint64_t(w_cap)) * 8 + 64);
+        launch_quirk_finish(f->img, ws.q_bases.as<char>(), ws.q_voff.as<uint64_t>(), n_v, qst + 4, ws.q_vstart.as<uint32_t>(),
+                            n_list, ws.q_vcode_off.as<uint64_t>(), ws.codes2.as<uint64_t>(), ws.q_spur.as<uint64_t>(),
+                            ws.q_spur_cnt.as<uint32_t>(), w_cap, ws.q_out_off.as<uint64_t>(), ws.q_out.as<uint64_t>(),
+                            ws.aux1.as<uint64_t>(), ws.aux2.as<uint64_t>(), ws.q_tmp.p, ws.q_tmp.cap, s);
+        launch_quirk_emit(ws.q_vcode_off.as<uint64_t>(), ws.codes2.as<uint64_t>(), ws.q_spur.as<uint64_t>(),
+                          ws.q_spur_cnt.as<uint32_t>(), w_cap, n_v, qst + 4, ws.q_out_off.as<uint64_t>(), q_bytes,
+                          ws.q_out.as<uint64_t>(), s);
+        f->stats.kernel_launches += 6;
+        std::vector<uint64_t> counts(n_list), q_off(n_list);
+        CK(cudaMemcpyAsync(q_off.data(), ws.aux1.p, n_list * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(counts.data(), ws.aux2.p, n_list * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        qtr.mark(s, "episodes + per-run layout + emit");
         // final layout + where each contig's codes come from (clean layout or quirk scratch)
         std::vector<uint64_t> src_off(n_contigs);
         uint64_t new_total = 0, clean_run = 0;
@@ -736,8 +813,8 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         CK(cudaMemcpyAsync(ws.aux3.p, src_off.data(), n_contigs * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ws.code_off.p, code_offsets, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, s));
         launch_assemble(ws.tmp.as<uint64_t>(), ws.code_off.as<uint64_t>(), ws.codes.as<uint64_t>(),
-                        ws.codes2.as<uint64_t>(), ws.aux3.as<uint64_t>(), ws.dirty.as<uint8_t>(),
-                        n_contigs, s);
+                        ws.q_out.as<uint64_t>(), ws.aux3.as<uint64_t>(), ws.dirty.as<uint8_t>(),
+                        n_contigs, new_total, s);
         f->stats.kernel_launches += 1;
         if (want_runs) {
             reserve_runs(ws, new_total + 16);
@@ -748,9 +825,11 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
             f->stats.d2h_bytes = runs_done * 12 + n_contigs + list.size() * 8 + 40;
             return LPHB_OK;
         }
+        qtr.mark(s, "assemble");
         if (new_total) CK(cudaMemcpyAsync(codes, ws.tmp.p, new_total * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
+        qtr.mark(s, "final D2H");
         f->stats.d2h_bytes = new_total * 8 + n_contigs + list.size() * 8 + 32;
         return LPHB_OK;
     });
@@ -874,19 +953,6 @@ ScanSession& scan_session(int device) {
     if (!d.scan) d.scan = new ScanSession();
     return *d.scan;
 }
-
-// LPHB_SCAN_TRACE=1: per-stage wall times of the scan on stderr (each mark synchronizes the stream)
-struct ScanTrace {
-    bool on = getenv("LPHB_SCAN_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    void mark(cudaStream_t s, const char* what) {
-        if (!on) return;
-        if (s) cudaStreamSynchronize(s);
-        auto n = std::chrono::steady_clock::now();
-        fprintf(stderr, "[lphb scan] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
-        t = n;
-    }
-};
 
 // The scan of one batch whose bases and offsets are ALREADY on the device (d_bases indexed by the
 // offsets, i.e. d_bases + offsets[0] is the first base): leaves the records (scan order) and the

@@ -48,17 +48,26 @@ bool launch_scan_records_tiled(uint32_t k, uint32_t m, uint64_t seed, DevBatch c
                                cudaStream_t stream);
 bool scan_tiled_available(uint32_t k, uint32_t m);
 
-// Exact sequential emulation of the reference's streaming loop for contigs that contain
-// non-ACGT bytes (one thread per listed contig).  out_off[j] = where contig list[j] may write
-// (capacity L - m + 1 each); counts[j] receives how many codes it produced.
-void launch_query_quirk(DevImage const& img, const char* bases, const uint64_t* offsets,
-                        const uint64_t* list, uint64_t n_list, const uint64_t* out_off,
-                        uint64_t* out, uint64_t* counts, cudaStream_t stream);
+// Contigs with non-ACGT bytes, run-parallel (quirk_kernels.cu).  All asynchronous on `stream`.
+void launch_gather_contigs(const char* bases, const uint64_t* offsets, const uint64_t* list, const uint64_t* dst_off,
+                           uint64_t n_list, uint64_t total_bytes, char* dst, cudaStream_t stream);
+uint64_t quirk_tmp_bytes(uint64_t n);
+void launch_find_runs(const char* d_bases, uint64_t n, const uint64_t* d_starts, uint64_t n_list, uint8_t* d_flag,
+                      uint64_t* d_voff, unsigned long long* d_n_v, uint32_t* d_vstart, void* d_tmp, uint64_t tmp_bytes,
+                      cudaStream_t stream);
+void launch_quirk_finish(DevImage const& img, const char* d_bases, const uint64_t* d_voff, uint64_t n_v_host,
+                         const unsigned long long* d_n_v, const uint32_t* d_vstart, uint64_t n_list,
+                         const uint64_t* d_vcode_off, const uint64_t* d_vcodes, uint64_t* d_spur, uint32_t* d_spur_cnt,
+                         uint32_t w_cap, uint64_t* d_out_off, uint64_t* d_out, uint64_t* d_q_off, uint64_t* d_counts,
+                         void* d_tmp, uint64_t tmp_bytes, cudaStream_t stream);
+void launch_quirk_emit(const uint64_t* d_vcode_off, const uint64_t* d_vcodes, const uint64_t* d_spur,
+                       const uint32_t* d_spur_cnt, uint32_t w_cap, uint64_t n_v_host, const unsigned long long* d_n_v,
+                       const uint64_t* d_out_off, uint64_t total_hint, uint64_t* d_out, cudaStream_t stream);
 
-// dst[dst_off[c] .. +cnt[c]) = src_c[src_off[c] ..) where src_c = from_b[c] ? src_b : src_a.
+// dst[dst_off[c] .. dst_off[c+1]) = src_c[src_off[c] ..) where src_c = from_b[c] ? src_b : src_a (`total` = dst_off[n_contigs])
 void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src_a,
                      const uint64_t* src_b, const uint64_t* src_off, const uint8_t* from_b,
-                     uint64_t n_contigs, cudaStream_t stream);
+                     uint64_t n_contigs, uint64_t total, cudaStream_t stream);
 
 // Run-length form of a code stream on the device (runs_kernels.cu): codes[0..n), n < 2^31 -> 12-byte
 // records {u64 first, i32 n} (n > 0 ascending, n < 0 descending), never across a contig start.

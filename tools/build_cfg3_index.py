@@ -14,12 +14,17 @@ from lphash_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_500_000_000
+# A random genome of 2.5e9 bases holds a repeated 31-mer with probability ~0.5 (n^2 / (2 * 4^31) = 0.68
+# expected pairs); the reference's build then fails in PTHash ("seed did not work": the repeated k-mer is a
+# duplicate key of fallback_kmer_order).  The seed is therefore part of the workload definition:
+# tools/build_cfg3_index.py <n> <seed> tries one, bench_cache/cfg3_seed.txt records the one that built.
+seed = int(sys.argv[2], 0) if len(sys.argv) > 2 else 0x5EED0013
 cache = os.path.join(ROOT, "bench_cache")
 os.makedirs(cache, exist_ok=True)
 tag = f"cfg3_n{n}_k31_m20_u64"
 lph = os.path.join(cache, tag + ".lph")
 t0 = time.time()
-bases, offsets = synth.unitigs(n, 31, 20, seed=0x5EED0003)
+bases, offsets = synth.unitigs(n, 31, 20, seed=seed)
 print(f"unitigs: {len(offsets) - 1} contigs, {len(bases)} bases ({time.time() - t0:.0f}s)", flush=True)
 fa = os.path.join(cache, tag + ".fa")
 synth.write_fasta(fa, bases, offsets)
@@ -28,4 +33,5 @@ print(f"fasta written ({time.time() - t0:.0f}s)", flush=True)
 csv = ref.build(fa, 31, 20, lph + ".tmp", bits=64, c=5.0, threads=8, max_memory_gb=24, tmp_dir=cache)
 os.replace(lph + ".tmp", lph)
 os.remove(fa)
-print(f"build-p: {csv} ({time.time() - t0:.0f}s), {os.path.getsize(lph)} bytes", flush=True)
+open(os.path.join(cache, "cfg3_seed.txt"), "w").write(hex(seed) + "\n")
+print(f"build-p (genome seed {seed:#x}): {csv} ({time.time() - t0:.0f}s), {os.path.getsize(lph)} bytes", flush=True)
