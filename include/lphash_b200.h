@@ -83,6 +83,16 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets,
                       uint64_t n_contigs, uint64_t* codes, uint64_t codes_capacity,
                       uint64_t* code_offsets, uint64_t* n_codes);
 
+/* The reference's NON-streaming branch, hf(seq, len, false) (include/partitioned_mphf.hpp:185-195;
+ * pass 2 of query-p, src/query.cpp:72, and `--check`, include/mphf_utils.hpp:56,85): the stateless
+ * evaluation of every window of k bytes, where a non-ACGT byte counts as 'A'
+ * (include/mphf_utils.hpp:108).  Same arguments as lphb_query_stream; contig c always yields
+ * max(0, L-k+1) codes (the reference itself is undefined for L < k).  On ACGT-only input the two
+ * branches return the same codes.                                                  */
+int lphb_query_nonstreaming(lphb_mphf* f, const char* bases, const uint64_t* offsets,
+                            uint64_t n_contigs, uint64_t* codes, uint64_t codes_capacity,
+                            uint64_t* code_offsets, uint64_t* n_codes);
+
 /* Same call with the codes returned in RUN-LENGTH form: consecutive k-mers of a super-k-mer get
  * consecutive codes (include/partitioned_mphf.hpp:131-145: local_rank +-1 per k-mer), so the vector
  * the reference returns is a sequence of arithmetic runs.  `runs` receives packed 12-byte records

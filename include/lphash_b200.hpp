@@ -28,6 +28,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -112,13 +113,13 @@ public:
     uint32_t get_m() const noexcept { return info_.m; }
     lphb_info const& info() const noexcept { return info_; }
 
-    // hf(contig, length, streaming).  Both reference branches give the same codes on ACGT-only
-    // input; the streaming branch — non-ACGT quirk included — is what is computed.
-    std::vector<uint64_t> operator()(const char* contig, std::size_t length,
-                                     bool /*streaming*/ = true) const {
+    // hf(contig, length, streaming).  streaming = true: the reference's streaming branch, non-ACGT quirk
+    // included (partitioned_mphf.hpp:73-184); false: its non-streaming branch, where a non-ACGT byte
+    // counts as 'A' (partitioned_mphf.hpp:185-195, mphf_utils.hpp:108).  Same codes on ACGT-only input.
+    std::vector<uint64_t> operator()(const char* contig, std::size_t length, bool streaming = true) const {
         const uint64_t offsets[2] = {0, uint64_t(length)};
         std::vector<uint64_t> codes, code_offsets;
-        query_batch(contig, offsets, 1, codes, code_offsets);
+        query_batch(contig, offsets, 1, codes, code_offsets, streaming);
         return codes;
     }
     std::vector<uint64_t> operator()(std::string const& contig, bool streaming = true) const {
@@ -130,7 +131,8 @@ public:
     // codes = all contigs' codes in contig order; contig c owns
     // [code_offsets[c], code_offsets[c+1]).
     void query_batch(const char* bases, const uint64_t* offsets, uint64_t n_contigs,
-                     std::vector<uint64_t>& codes, std::vector<uint64_t>& code_offsets) const {
+                     std::vector<uint64_t>& codes, std::vector<uint64_t>& code_offsets,
+                     bool streaming = true) const {
         if (!h_) throw std::runtime_error("lphash_b200::mphf: no index loaded");
         // a contig with non-ACGT bytes can emit up to L-m+1 codes (reference quirk)
         uint64_t cap = 0;
@@ -141,8 +143,9 @@ public:
         codes.resize(cap);
         code_offsets.resize(n_contigs + 1);
         uint64_t n = 0;
-        int rc = lphb_query_stream(h_, bases, offsets, n_contigs, codes.data(), cap,
-                                   code_offsets.data(), &n);
+        int rc = streaming ? lphb_query_stream(h_, bases, offsets, n_contigs, codes.data(), cap, code_offsets.data(), &n)
+                           : lphb_query_nonstreaming(h_, bases, offsets, n_contigs, codes.data(), cap,
+                                                     code_offsets.data(), &n);
         if (rc != LPHB_OK) detail::raise("lphash_b200::mphf::operator()", rc);
         codes.resize(n);
     }
@@ -156,6 +159,34 @@ private:
     }
     lphb_mphf* h_ = nullptr;
     lphb_info info_{};
+};
+
+// Serializes any object that speaks the essentials visitor protocol (`template <class V> void visit(V&)`)
+// into memory, byte for byte what essentials::save writes to a file (essentials.hpp:326-366: PODs raw,
+// std::vector<T> = size_t count + elements): the `.lph` image of a reference lphash::mphf without a
+// round trip through the file system.  mphf::load(image, nbytes) takes the result.
+struct memory_saver {
+    std::vector<unsigned char> bytes;
+    template <typename T>
+    void visit(T& val) {
+        if constexpr (std::is_pod<T>::value) {
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(&val);
+            bytes.insert(bytes.end(), p, p + sizeof(T));
+        } else {
+            val.visit(*this);
+        }
+    }
+    template <typename T, typename Allocator>
+    void visit(std::vector<T, Allocator>& vec) {
+        size_t n = vec.size();
+        visit(n);
+        if constexpr (std::is_pod<T>::value) {
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(vec.data());
+            bytes.insert(bytes.end(), p, p + n * sizeof(T));
+        } else {
+            for (auto& v : vec) visit(v);
+        }
+    }
 };
 
 namespace minimizer {

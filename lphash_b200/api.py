@@ -52,7 +52,7 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
            "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify",
            "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags",
-           "lphb_scan_superkmers_device", "lphb_copy_to_host"]
+           "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming"]
 
 _lib = None
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.lphb_mphf_info.argtypes = [p, C.POINTER(Info)]
     L.lphb_mphf_stats.argtypes = [p, C.POINTER(Stats)]
     L.lphb_query_stream.argtypes = [p, p, p, u64, p, u64, p, C.POINTER(u64)]
+    L.lphb_query_nonstreaming.argtypes = [p, p, p, u64, p, u64, p, C.POINTER(u64)]
     L.lphb_query_stream_device.argtypes = [p, p, p, p, u64, p, u64, p, p, p]
     L.lphb_query_stream_runs.argtypes = [p, p, p, u64, p, u64, C.POINTER(u64), p, C.POINTER(u64)]
     L.lphb_expand_runs.argtypes = [p, u64, p, u64, C.POINTER(u64), i32]
@@ -170,17 +171,18 @@ class Mphf:
     # -- queries -----------------------------------------------------------------------------
     def __call__(self, contig, streaming: bool = True) -> np.ndarray:
         """hf(contig, len, streaming): hash codes of the contig's k-mers.  The two modes of the
-        reference agree on ACGT-only input; `streaming=False` is served by the
-        same device path (its reference branch maps non-ACGT to 'A', which is not reproduced)."""
+        reference agree on ACGT-only input; `streaming=False` is the reference's
+        non-streaming branch, where a non-ACGT byte counts as 'A' (lphb_query_nonstreaming)."""
         if isinstance(contig, str):
             contig = contig.encode()
         bases = np.frombuffer(bytes(contig), dtype=np.uint8)
         offsets = np.array([0, len(bases)], dtype=np.uint64)
-        codes, _ = self.query_batch(bases, offsets)
+        codes, _ = self.query_batch(bases, offsets, streaming=streaming)
         return codes
 
-    def query_batch(self, bases, offsets, out: np.ndarray | None = None):
-        """One C-ABI call for a batch: returns (codes, code_offsets) with HOST arrays in and out."""
+    def query_batch(self, bases, offsets, out: np.ndarray | None = None, streaming: bool = True):
+        """One C-ABI call for a batch: returns (codes, code_offsets) with HOST arrays in and out.
+        streaming=False: the reference's non-streaming branch (non-ACGT bytes count as 'A')."""
         bases, offsets = _as_batch(bases, offsets)
         n = len(offsets) - 1
         lens = np.diff(offsets).astype(np.int64)
@@ -193,8 +195,9 @@ class Mphf:
         codes = np.empty(max(cap, 1), dtype=np.uint64) if out is None else out
         code_off = np.empty(n + 1, dtype=np.uint64)
         total = C.c_uint64(0)
-        _check(lib().lphb_query_stream(self._h, bases.ctypes.data, offsets.ctypes.data, n,
-                                       codes.ctypes.data, cap, code_off.ctypes.data, C.byref(total)))
+        fn = lib().lphb_query_stream if streaming else lib().lphb_query_nonstreaming
+        _check(fn(self._h, bases.ctypes.data, offsets.ctypes.data, n,
+                  codes.ctypes.data, cap, code_off.ctypes.data, C.byref(total)))
         return codes[: total.value], code_off
 
     def query_batch_runs(self, bases, offsets, out: np.ndarray | None = None):

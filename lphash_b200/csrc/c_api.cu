@@ -496,6 +496,9 @@ struct RunSink {
     void* runs = nullptr;        // null: codes mode
     uint64_t capacity = 0;
     uint64_t* n_runs = nullptr;
+    // the reference's NON-streaming branch (include/partitioned_mphf.hpp:185-195): every window of k bytes is a
+    // k-mer, a non-ACGT byte counts as 'A' (include/mphf_utils.hpp:108); no streaming state, hence no quirk
+    bool non_streaming = false;
 };
 
 // scratch of the run-length pass for a stream of n codes
@@ -617,6 +620,7 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         };
         if (!pipelined) {
             CK(cudaMemcpyAsync(ws.bases.p, bases + first, span, cudaMemcpyHostToDevice, s));
+            if (sink.non_streaming) launch_sanitize(ws.bases.as<char>(), span, s);
             ws.tile.reserve(query_tiled_ws_bytes(span));
             b.tile_ws = ws.tile.p;
             b.tile_ws_bytes = ws.tile.cap;
@@ -641,9 +645,11 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
                 if (j < 2) CK(cudaStreamWaitEvent(st, ws.ev_ready, 0));
                 const uint64_t c0 = cuts[j], c1 = cuts[j + 1];
                 const uint64_t b0 = offsets[c0], b1 = offsets[c1];
-                if (b1 > b0)
+                if (b1 > b0) {
                     CK(cudaMemcpyAsync(ws.bases.as<char>() + (b0 - first), bases + b0, b1 - b0,
                                        cudaMemcpyHostToDevice, st));
+                    if (sink.non_streaming) launch_sanitize(ws.bases.as<char>() + (b0 - first), b1 - b0, st);
+                }
                 DevBatch bj = b;
                 bj.offsets = b.offsets + c0;
                 bj.code_off = b.code_off + c0;
@@ -844,6 +850,14 @@ int lphb_query_stream(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
                       uint64_t* n_codes) {
     if (!f || !offsets || !code_offsets || !n_codes) return fail(LPHB_E_ARG, "null argument");
     return query_stream_host(f, bases, offsets, n_contigs, codes, codes_capacity, code_offsets, n_codes, RunSink{});
+}
+
+int lphb_query_nonstreaming(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                            uint64_t* codes, uint64_t codes_capacity, uint64_t* code_offsets, uint64_t* n_codes) {
+    if (!f || !offsets || !code_offsets || !n_codes) return fail(LPHB_E_ARG, "null argument");
+    RunSink sink;
+    sink.non_streaming = true;
+    return query_stream_host(f, bases, offsets, n_contigs, codes, codes_capacity, code_offsets, n_codes, sink);
 }
 
 int lphb_query_stream_runs(lphb_mphf* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs,

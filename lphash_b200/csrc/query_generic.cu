@@ -88,6 +88,13 @@ __global__ void __launch_bounds__(256) k_query_generic(const __grid_constant__ D
     }
 }
 
+// bytes outside ACGT/acgt/U/u -> 'A' (what the reference's non-streaming branch makes of them:
+// include/mphf_utils.hpp:108, seq_nt4_table[c] & 3)
+__global__ void k_sanitize(char* bases, uint64_t n) {
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+        if (nt4(uint8_t(bases[i])) > 3) bases[i] = 'A';
+}
+
 __global__ void k_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status) {
     unsigned long long local = 0;
     for (uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; c < n;
@@ -127,6 +134,13 @@ void launch_query_generic(DevImage const& img, DevBatch const& b, cudaStream_t s
     uint64_t blocks = (span + 255) / 256;
     if (blocks > 148ull * 64) blocks = 148ull * 64;
     k_query_generic<<<unsigned(blocks), 256, 0, stream>>>(img, b);
+}
+
+void launch_sanitize(char* d_bases, uint64_t n, cudaStream_t stream) {
+    if (!n) return;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    k_sanitize<<<unsigned(blocks), 256, 0, stream>>>(d_bases, n);
 }
 
 void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status,

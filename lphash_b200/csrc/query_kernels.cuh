@@ -76,6 +76,9 @@ void launch_runs(const uint64_t* codes, uint64_t n, const uint64_t* code_off, ui
                  uint8_t* d_start, uint8_t* d_head, uint32_t* d_rank, uint32_t* d_head_at, void* d_tmp,
                  uint64_t tmp_bytes, uint8_t* d_runs, unsigned long long* d_n_runs, cudaStream_t stream);
 
+// non-ACGT bytes -> 'A' in place (the reference's non-streaming branch, include/mphf_utils.hpp:108)
+void launch_sanitize(char* d_bases, uint64_t n, cudaStream_t stream);
+
 // status[1] += number of set flags in dirty[0..n)
 void launch_count_dirty(const uint8_t* dirty, uint64_t n, unsigned long long* status,
                         cudaStream_t stream);

@@ -20,7 +20,8 @@ if [ ! -d "$REF/include" ]; then
   exit 0
 fi
 mkdir -p "$OUT"
-CXXFLAGS="-std=c++17 -O3 -march=x86-64-v3 -mbmi2 -msse4.2 -pthread -include memory -w -fPIC"
+# -DNDEBUG: the reference builds as CMake "Release" by default (CMakeLists.txt:5-7), i.e. with its asserts off
+CXXFLAGS="-std=c++17 -O3 -DNDEBUG -march=x86-64-v3 -mbmi2 -msse4.2 -pthread -include memory -w -fPIC"
 SRCS="src/constants.cpp src/quartet_wtree.cpp src/minimizer.cpp src/partitioned_mphf.cpp src/mphf_utils.cpp"
 build_flavour() {
   local bits="$1" type="$2"

@@ -432,3 +432,33 @@ def test_scan_records_cross_tile_boundaries():
         want = want.copy()
         want["id"] += np.uint64(12345)
         assert np.array_equal(got, want), (k, m)
+
+
+@pytest.mark.parametrize("name", ["k31_m20_u64", "k63_m24_u128", "k25_m13_u64"])
+def test_non_streaming_branch_matches_the_reference(name, handles):
+    """hf(contig, len, streaming=false) (include/partitioned_mphf.hpp:185-195): every window of k bytes,
+    a non-ACGT byte counting as 'A' (include/mphf_utils.hpp:108) - against the unmodified reference
+    (oracle/_ref), contig by contig, on the golden query batch (N runs, junk bytes, lower case)."""
+    from oracle import ref
+    g = load_golden(name)
+    if not ref.available(g.bits):
+        pytest.skip("oracle/_ref not built")
+    f = handles(name)
+    r = ref.RefMphf(g.lph, g.bits)
+    contigs = [c for c in g.contigs() if len(c) >= g.k]  # the reference is undefined below k (length-k+1 underflows)
+    clean = dict(zip(g.contigs(), g.is_clean()))
+    n_dirty = 0
+    for c in contigs:
+        want = r.query(c, streaming=False)
+        got = f(c, streaming=False)
+        assert len(want) == len(c) - g.k + 1
+        assert np.array_equal(got, want)
+        n_dirty += 0 if clean[c] else 1
+    assert n_dirty >= 5
+    # batch form: same codes, clean layout
+    bases = np.frombuffer(b"".join(contigs), dtype=np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    codes, code_off = f.query_batch(bases, offsets, streaming=False)
+    assert np.array_equal(np.diff(code_off).astype(np.int64), np.array([len(c) - g.k + 1 for c in contigs]))
+    assert np.array_equal(codes, np.concatenate([r.query(c, streaming=False) for c in contigs]))
+    r.close()
