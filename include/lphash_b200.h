@@ -53,6 +53,8 @@ typedef struct lphb_info {
     uint64_t fallback_keys; /* k-mers handled by fallback_kmer_order */
     uint64_t file_bytes;    /* size of the .lph image parsed                                    */
     uint64_t device_bytes;  /* bytes of HBM the device image occupies                           */
+    double load_host_ms;    /* load time: parsing the image and building the flat arrays (host)  */
+    double load_h2d_ms;     /* load time: device allocation + the one host-to-device copy        */
 } lphb_info;
 
 const char* lphb_last_error(void);
@@ -66,6 +68,14 @@ int lphb_device_count(int* count);
 int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out);
 int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device,
                           lphb_mphf** out);
+/* The same for the UNPARTITIONED variant, lphash::mphf_alt (`build-u` / `query-u`: include/
+ * unpartitioned_mphf.hpp:198-210 is the file format, src/unpartitioned_mphf.cpp:191-206 the probe).  The
+ * handle then serves every query entry point below exactly like a partitioned one: mphf_alt's
+ * operator() (include/unpartitioned_mphf.hpp:72-192) is the same streaming loop over another probe.
+ * (lphb_info: n_maximal and the *_start fields are 0.)                                              */
+int lphb_mphf_alt_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out);
+int lphb_mphf_alt_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device,
+                              lphb_mphf** out);
 int lphb_mphf_free(lphb_mphf* f);
 int lphb_mphf_info(const lphb_mphf* f, lphb_info* info);
 

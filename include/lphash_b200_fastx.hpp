@@ -35,21 +35,40 @@ struct Batch {
     uint64_t n_records() const { return offsets.empty() ? 0 : offsets.size() - 1; }
 };
 
-// Appends every record of `data[0..n)` to `out`.  Returns the number of records appended.
-inline uint64_t parse(const char* data, size_t n, Batch& out) {
+// Appends the records of `data[0..n)` to `out` and returns how many bytes were consumed.
+//   final = true : the text ends here (end of file): every record kseq_read would return is appended, n is returned.
+//   final = false: more text follows.  A record is only trusted once the NEXT record's header line has been seen
+//                  (a FASTA sequence or a FASTQ quality string may continue in the next chunk), so the last record
+//                  in the chunk is held back: the return value is the position of its header character and the
+//                  caller passes data[ret..n) again, followed by the next chunk.
+// *stopped is set when kseq_read would have returned an error (FASTQ quality string of the wrong length, with more
+// text after it): the reference's `while (kseq_read(seq) >= 0)` loop ends there, and so must the caller.
+inline size_t parse_some(const char* data, size_t n, Batch& out, bool final, bool* stopped = nullptr,
+                         uint64_t* added_out = nullptr) {
     if (out.offsets.empty()) out.offsets.push_back(0);
+    if (stopped) *stopped = false;
     const char* p = data;
     const char* const end = data + n;
     uint64_t added = 0;
+    size_t last_seq_begin = 0;          // where the bases of the last accepted record start in out.bases
+    const char* last_rec_start = nullptr;  // its header character
     auto line_end = [&](const char* q) -> const char* {
         const void* e = q < end ? std::memchr(q, '\n', size_t(end - q)) : nullptr;
         return e ? static_cast<const char*>(e) : end;
+    };
+    auto done = [&](size_t consumed) {
+        if (added_out) *added_out = added;
+        return consumed;
     };
     // skip to the first header character
     while (p < end && *p != '>' && *p != '@') ++p;
     while (p < end) {
         // p is at a header character: skip the header line
-        if (p + 1 == end) break;  // a bare header character at the very end: kseq reports end of file
+        const char* const rec_start = p;
+        if (p + 1 == end) {  // a bare header character at the very end: kseq reports end of file
+            if (final) break;
+            return done(size_t(rec_start - data));
+        }
         p = line_end(p);
         if (p < end) ++p;
         const size_t seq_begin = out.bases.size();
@@ -90,11 +109,28 @@ inline uint64_t parse(const char* data, size_t n, Batch& out) {
                 out.bases.resize(seq_begin);
                 out.offsets.pop_back();
                 --added;
-                break;
+                if (!final && p == end) return done(size_t(rec_start - data));  // perhaps only cut by the chunk
+                if (stopped) *stopped = true;
+                return done(n);
             }
             while (p < end && *p != '>' && *p != '@') ++p;  // to the next header character
         }
+        last_seq_begin = seq_begin;
+        last_rec_start = rec_start;
     }
+    if (!final && last_rec_start) {  // hold the last record back: it may go on in the next chunk
+        out.bases.resize(last_seq_begin);
+        out.offsets.pop_back();
+        --added;
+        return done(size_t(last_rec_start - data));
+    }
+    return done(n);
+}
+
+// Appends every record of `data[0..n)` (a whole file) to `out`.  Returns the number of records appended.
+inline uint64_t parse(const char* data, size_t n, Batch& out) {
+    uint64_t added = 0;
+    parse_some(data, n, out, true, nullptr, &added);
     return added;
 }
 
@@ -135,6 +171,138 @@ inline uint64_t read_file(std::string const& path, Batch& out) {
         throw std::runtime_error(path + " is gzip-compressed: build with -DLPHASH_B200_WITH_ZLIB -lz");
 #endif
     return parse(text.data(), text.size(), out);
+}
+
+// ---- streaming ingest --------------------------------------------------------------------------------------
+// The file is inflated / read in chunks of `chunk_bytes` on ONE background thread, which also splits the
+// records (parse_some) into batches; `on_batch(Batch&)` runs on the calling thread, in file order, while the
+// background thread is already producing the next batch (two batches in flight).  With the GPU call inside
+// on_batch, inflate + parse of chunk i+1 overlap the H2D copy, the kernels and the D2H copy of chunk i: this
+// is the overlap the reference's timed loop (gz + kseq + hf per record, src/query.cpp:48-56) cannot have.
+// Returns the number of records delivered.  zlib inflates one stream on one core (~0.3 GB/s of text); a plain
+// text file is bounded by the parser (memchr, a few GB/s).
+}  // namespace fastx
+}  // namespace lphash_b200
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+namespace lphash_b200 {
+namespace fastx {
+
+template <class OnBatch>
+uint64_t stream_file(std::string const& path, size_t chunk_bytes, OnBatch&& on_batch) {
+    if (chunk_bytes < 16) chunk_bytes = 16;
+    struct Slot {
+        Batch batch;
+        bool full = false;
+    } slots[2];
+    std::mutex mu;
+    std::condition_variable cv;
+    bool eof = false;
+    std::string error;
+    std::thread producer([&]() {
+        try {
+#ifdef LPHASH_B200_WITH_ZLIB
+            gzFile f = gzopen(path.c_str(), "rb");  // transparently reads uncompressed files too
+            if (!f) throw std::runtime_error("cannot open " + path);
+            gzbuffer(f, 1u << 20);
+            auto read_some = [&](char* dst, size_t want) -> size_t {
+                int got = gzread(f, dst, unsigned(want > (1u << 30) ? (1u << 30) : want));
+                if (got < 0) throw std::runtime_error("read error in " + path);
+                return size_t(got);
+            };
+#else
+            std::FILE* f = std::fopen(path.c_str(), "rb");
+            if (!f) throw std::runtime_error("cannot open " + path);
+            auto read_some = [&](char* dst, size_t want) -> size_t { return std::fread(dst, 1, want, f); };
+#endif
+            std::vector<char> text;  // carry (the record held back) + the next chunk
+            size_t carry = 0;
+            int which = 0;
+            bool more = true, stopped = false;
+            while (more && !stopped) {
+                text.resize(carry + chunk_bytes);
+                size_t got = 0;
+                while (got < chunk_bytes) {  // fill the chunk (gzread may return short counts)
+                    size_t r = read_some(text.data() + carry + got, chunk_bytes - got);
+                    if (r == 0) {
+                        more = false;
+                        break;
+                    }
+                    got += r;
+                }
+#ifndef LPHASH_B200_WITH_ZLIB
+                if (carry == 0 && got >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b)
+                    throw std::runtime_error(path + " is gzip-compressed: build with -DLPHASH_B200_WITH_ZLIB -lz");
+#endif
+                const size_t n = carry + got;
+                Slot& s = slots[which];
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !s.full; });
+                }
+                s.batch.bases.clear();
+                s.batch.offsets.clear();
+                const size_t used = parse_some(text.data(), n, s.batch, !more, &stopped);
+                carry = n - used;
+                if (carry && used) std::memmove(text.data(), text.data() + used, carry);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    s.full = true;
+                }
+                cv.notify_all();
+                which ^= 1;
+            }
+#ifdef LPHASH_B200_WITH_ZLIB
+            gzclose(f);
+#else
+            std::fclose(f);
+#endif
+        } catch (std::exception const& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            error = e.what();
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            eof = true;
+        }
+        cv.notify_all();
+    });
+    uint64_t delivered = 0;
+    int which = 0;
+    for (;;) {
+        Slot& s = slots[which];
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return s.full || eof; });
+            if (!s.full) break;  // producer finished and this slot was never filled
+        }
+        try {
+            if (s.batch.n_records()) on_batch(s.batch);
+        } catch (...) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                s.full = false;
+                slots[which ^ 1].full = false;
+            }
+            cv.notify_all();
+            producer.join();  // (it stops at its next wait: both slots are free; the file is read to the end)
+            throw;
+        }
+        delivered += s.batch.n_records();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            s.full = false;
+        }
+        cv.notify_all();
+        which ^= 1;
+    }
+    producer.join();
+    if (!error.empty()) throw std::runtime_error(error);
+    return delivered;
 }
 
 }  // namespace fastx

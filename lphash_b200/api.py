@@ -38,7 +38,8 @@ class Info(C.Structure):
                 ("mm_seed", C.c_uint64), ("nkmers", C.c_uint64), ("distinct_minimizers", C.c_uint64),
                 ("n_maximal", C.c_uint64), ("right_coll_sizes_start", C.c_uint64),
                 ("none_sizes_start", C.c_uint64), ("none_pos_start", C.c_uint64),
-                ("fallback_keys", C.c_uint64), ("file_bytes", C.c_uint64), ("device_bytes", C.c_uint64)]
+                ("fallback_keys", C.c_uint64), ("file_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
+                ("load_host_ms", C.c_double), ("load_h2d_ms", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -52,7 +53,8 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_query_stream_device", "lphb_scan_superkmers", "lphb_colliding_kmers",
            "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify",
            "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags",
-           "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming"]
+           "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming",
+           "lphb_mphf_alt_load_file", "lphb_mphf_alt_load_memory"]
 
 _lib = None
 
@@ -72,6 +74,8 @@ def lib() -> C.CDLL:
     L.lphb_device_count.argtypes = [C.POINTER(C.c_int)]
     L.lphb_mphf_load_file.argtypes = [C.c_char_p, i32, i32, C.POINTER(p)]
     L.lphb_mphf_load_memory.argtypes = [p, u64, i32, i32, C.POINTER(p)]
+    L.lphb_mphf_alt_load_file.argtypes = [C.c_char_p, i32, i32, C.POINTER(p)]
+    L.lphb_mphf_alt_load_memory.argtypes = [p, u64, i32, i32, C.POINTER(p)]
     L.lphb_mphf_free.argtypes = [p]
     L.lphb_mphf_info.argtypes = [p, C.POINTER(Info)]
     L.lphb_mphf_stats.argtypes = [p, C.POINTER(Stats)]
@@ -136,6 +140,13 @@ class Mphf:
         """essentials::load(hf, path) (/root/reference/src/query.cpp:37)."""
         h = C.c_void_p()
         _check(lib().lphb_mphf_load_file(os.fsencode(path), kmer_bits, device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def load_alt(cls, path: str, kmer_bits: int = 64, device: int = 0) -> "Mphf":
+        """An unpartitioned LP-MPHF (the reference's `lphash::mphf_alt`, build-u / query-u)."""
+        h = C.c_void_p()
+        _check(lib().lphb_mphf_alt_load_file(os.fsencode(path), kmer_bits, device, C.byref(h)))
         return cls(h.value)
 
     @classmethod

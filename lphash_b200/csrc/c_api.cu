@@ -197,12 +197,15 @@ int guarded(F&& body) {
     }
 }
 
-int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_mphf** out) {
+int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_mphf** out, bool alt = false) {
     if (!out) return fail(LPHB_E_ARG, "out is null");
     *out = nullptr;
     return guarded([&]() -> int {
         ImageBuilder builder;
-        builder.parse(data, n, kmer_bits);  // host-only: format errors surface before any CUDA call
+        const auto t_parse0 = std::chrono::steady_clock::now();
+        if (alt) builder.parse_alt(data, n, kmer_bits);
+        else builder.parse(data, n, kmer_bits);  // host-only: format errors surface before any CUDA call
+        const auto t_parse1 = std::chrono::steady_clock::now();
         int count = 0;
         CK(cudaGetDeviceCount(&count));
         if (device < 0 || device >= count) return fail(LPHB_E_CUDA, "no such CUDA device");
@@ -215,6 +218,8 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
             CK(cudaMemcpy(f->d_arena, arena.data(), arena.size(), cudaMemcpyHostToDevice));
             f->img = builder.rebased(f->d_arena);
             f->arena_bytes = arena.size();
+            f->info.load_host_ms = std::chrono::duration<double, std::milli>(t_parse1 - t_parse0).count();
+            f->info.load_h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parse1).count();
             {
                 int max_persist = 0, max_window = 0;
                 cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
@@ -316,7 +321,9 @@ int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int
     return load_image(static_cast<const uint8_t*>(image), nbytes, kmer_bits, device, out);
 }
 
-int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out) {
+}  // extern "C"
+namespace {
+int load_file(const char* path, int kmer_bits, int device, lphb_mphf** out, bool alt) {
     if (!path) return fail(LPHB_E_ARG, "path is null");
     if (!out) return fail(LPHB_E_ARG, "out is null");
     *out = nullptr;
@@ -332,7 +339,20 @@ int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf**
         return LPHB_OK;
     });
     if (rc != LPHB_OK) return rc;
-    return load_image(buf.data(), uint64_t(buf.size()), kmer_bits, device, out);
+    return load_image(buf.data(), uint64_t(buf.size()), kmer_bits, device, out, alt);
+}
+}  // namespace
+extern "C" {
+
+int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out) {
+    return load_file(path, kmer_bits, device, out, false);
+}
+int lphb_mphf_alt_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out) {
+    return load_file(path, kmer_bits, device, out, true);
+}
+int lphb_mphf_alt_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device, lphb_mphf** out) {
+    if (!image) return fail(LPHB_E_ARG, "image is null");
+    return load_image(static_cast<const uint8_t*>(image), nbytes, kmer_bits, device, out, true);
 }
 
 int lphb_mphf_free(lphb_mphf* f) {

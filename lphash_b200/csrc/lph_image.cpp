@@ -2,10 +2,46 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 namespace lphb {
 
 namespace {
+
+// Load-time decoding is embarrassingly parallel once the running counters are turned into ranks: the loops
+// over buckets / Elias-Fano values below are cut into contiguous slices, one per host thread (LPHB_LOAD_THREADS,
+// default = hardware threads, at most 32).  An exception in a slice is rethrown on the calling thread.
+unsigned load_threads() {
+    if (const char* e = getenv("LPHB_LOAD_THREADS")) {
+        long v = strtol(e, nullptr, 10);
+        if (v >= 1) return unsigned(v > 64 ? 64 : v);
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    return hw == 0 ? 1 : (hw > 32 ? 32 : hw);
+}
+template <class F>
+void parallel_for(uint64_t n, uint64_t min_per_thread, F&& body) {  // body(begin, end, slice)
+    unsigned t = load_threads();
+    if (n / (min_per_thread ? min_per_thread : 1) < t) t = unsigned(n / (min_per_thread ? min_per_thread : 1));
+    if (t <= 1) {
+        body(uint64_t(0), n, 0u);
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(t);
+    for (unsigned i = 0; i < t; ++i)
+        pool.emplace_back([&, i] {
+            try {
+                body(n * i / t, n * (i + 1) / t, i);
+            } catch (...) {
+                err[i] = std::current_exception();
+            }
+        });
+    for (auto& th : pool) th.join();
+    for (auto& e : err)
+        if (e) std::rethrow_exception(e);
+}
 
 // MurmurHash2-64 of one 8-byte word (pthash hasher.hpp:46-110 with len == 8); used at load time
 // only, to pre-hash the pilot dictionaries.
@@ -100,20 +136,39 @@ std::vector<uint64_t> ImageBuilder::read_ef(Cursor& c) {
     c.vec<uint64_t>(no);  // overflow positions
     FileCompact low = c.compact();
     if (low.size != positions) throw FormatError("EF: darray positions != number of values");
-    std::vector<uint64_t> vals;
-    vals.reserve(positions);
-    for (uint64_t wi = 0; wi < nw && vals.size() < positions; ++wi) {
+    // set high bits before every slice of words (only bits below nbits count), then every slice decodes its own
+    auto word_at = [&](uint64_t wi) {
         uint64_t wv;
         std::memcpy(&wv, hw + 8 * wi, 8);
-        while (wv && vals.size() < positions) {
-            uint64_t pos = wi * 64 + uint64_t(__builtin_ctzll(wv));
-            wv &= wv - 1;
-            if (pos >= nbits) break;
-            uint64_t i = vals.size();
-            vals.push_back(((pos - i) << low.width) | low.get(i));
+        if ((wi + 1) * 64 > nbits) wv &= nbits > wi * 64 ? ((uint64_t(1) << (nbits - wi * 64)) - 1) : 0;
+        return wv;
+    };
+    const unsigned slices = load_threads();
+    std::vector<uint64_t> before(slices + 1, 0);
+    parallel_for(slices, 1, [&](uint64_t s0, uint64_t s1, unsigned) {
+        for (uint64_t sl = s0; sl < s1; ++sl) {
+            uint64_t cnt = 0;
+            for (uint64_t wi = nw * sl / slices; wi < nw * (sl + 1) / slices; ++wi) cnt += uint64_t(__builtin_popcountll(word_at(wi)));
+            before[sl + 1] = cnt;
         }
-    }
-    if (vals.size() != positions) throw FormatError("EF: fewer set bits than values");
+    });
+    for (unsigned sl = 0; sl < slices; ++sl) before[sl + 1] += before[sl];
+    if (before[slices] < positions) throw FormatError("EF: fewer set bits than values");
+    std::vector<uint64_t> vals(positions);
+    parallel_for(slices, 1, [&](uint64_t s0, uint64_t s1, unsigned) {
+        for (uint64_t sl = s0; sl < s1; ++sl) {
+            uint64_t i = before[sl];
+            for (uint64_t wi = nw * sl / slices; wi < nw * (sl + 1) / slices && i < positions; ++wi) {
+                uint64_t wv = word_at(wi);
+                while (wv && i < positions) {
+                    const uint64_t pos = wi * 64 + uint64_t(__builtin_ctzll(wv));
+                    wv &= wv - 1;
+                    vals[i] = ((pos - i) << low.width) | low.get(i);
+                    ++i;
+                }
+            }
+        }
+    });
     return vals;
 }
 
@@ -150,65 +205,99 @@ void ImageBuilder::build_buckets(Bits const& root, Bits const& left_right, Bits 
     // repeat the word of the key position free_slots sends them to (single_phf.hpp:61-63), so the
     // query needs no free-slot lookup.
     const uint64_t T = D + free_slots.size();
-    std::vector<uint64_t> e(T);
-    uint64_t n0 = 0, n1 = 0;              // zeros / ones of root seen so far
-    uint64_t r_left = 0, r_right = 0, r_max = 0, r_none = 0;
-    uint64_t max_base = 0;
-    for (uint64_t b = 0; b < D; ++b) {
-        bool msb = root.get(b);
-        uint64_t base = 0, kind = 0;
-        if (!msb) {
-            if (n0 >= left_right.nbits) throw FormatError("wavelet tree: left/right leaf too short");
-            bool lsb = left_right.get(n0++);
-            if (!lsb) {  // LEFT: g = EF[rank] + w*n_max, l = p
-                base = S(r_left++) + maxblock;
-                kind = 1;
-            } else {     // RIGHT or collision (size 0)
-                uint64_t v1 = S(rs + r_right), v2 = S(rs + r_right + 1);
-                ++r_right;
-                if (v2 == v1) {
-                    kind = 0;
-                } else {  // g = v1 + w*n_max, l = (k-m) - p
-                    base = v1 + maxblock + uint64_t(img_.k - img_.m);
+    BucketWriter e = begin_buckets(T);
+    if (left_right.nbits + max_none.nbits != D) throw FormatError("wavelet tree: leaves do not add up to the root");
+    // ones before every 64-bit word of the three bit vectors: the counters of a slice's first bucket are ranks
+    auto prefix_ones = [](Bits const& bv) {
+        const uint64_t nw = (bv.nbits + 63) / 64;
+        std::vector<uint64_t> cum(nw + 1, 0);
+        for (uint64_t w = 0; w < nw; ++w) {
+            uint64_t x = bv.words[w];
+            if ((w + 1) * 64 > bv.nbits) x &= (uint64_t(1) << (bv.nbits - w * 64)) - 1;
+            cum[w + 1] = cum[w] + uint64_t(__builtin_popcountll(x));
+        }
+        return cum;
+    };
+    auto rank1 = [](Bits const& bv, std::vector<uint64_t> const& cum, uint64_t pos) {  // ones in [0, pos), pos <= nbits
+        const uint64_t w = pos >> 6, r = pos & 63;
+        return cum[w] + (r ? uint64_t(__builtin_popcountll(bv.words[w] & ((uint64_t(1) << r) - 1))) : 0);
+    };
+    const std::vector<uint64_t> cum_root = prefix_ones(root), cum_lr = prefix_ones(left_right), cum_mn = prefix_ones(max_none);
+    if (rank1(root, cum_root, D) != max_none.nbits) throw FormatError("wavelet tree: root ones != size of the max/none leaf");
+    std::vector<uint64_t> slice_max(64, 0);
+    parallel_for(D, 1 << 16, [&](uint64_t b0, uint64_t b1, unsigned slice) {
+        uint64_t n1 = rank1(root, cum_root, b0), n0 = b0 - n1;  // ones / zeros of root before the slice
+        uint64_t r_right = rank1(left_right, cum_lr, n0), r_left = n0 - r_right;
+        uint64_t r_none = rank1(max_none, cum_mn, n1), r_max = n1 - r_none;
+        uint64_t max_base = 0;
+        for (uint64_t b = b0; b < b1; ++b) {
+            bool msb = root.get(b);
+            uint64_t base = 0, kind = 0;
+            if (!msb) {
+                bool lsb = left_right.get(n0++);
+                if (!lsb) {  // LEFT: g = EF[rank] + w*n_max, l = p
+                    base = S(r_left++) + maxblock;
+                    kind = 1;
+                } else {     // RIGHT or collision (size 0)
+                    uint64_t v1 = S(rs + r_right), v2 = S(rs + r_right + 1);
+                    ++r_right;
+                    if (v2 == v1) {
+                        kind = 0;
+                    } else {  // g = v1 + w*n_max, l = (k-m) - p
+                        base = v1 + maxblock + uint64_t(img_.k - img_.m);
+                        kind = 2;
+                    }
+                }
+            } else {
+                bool lsb = max_none.get(n1++);
+                if (!lsb) {  // MAXIMAL: g = w*rank, l = p
+                    base = w * r_max++;
+                    kind = 1;
+                } else {     // NONE: g = EF[none_sizes_start+rank] + w*n_max, l = diff(none_pos) - p
+                    base = S(ns + r_none) + maxblock + (S(np + r_none + 1) - S(np + r_none));
+                    ++r_none;
                     kind = 2;
                 }
             }
-        } else {
-            if (n1 >= max_none.nbits) throw FormatError("wavelet tree: max/none leaf too short");
-            bool lsb = max_none.get(n1++);
-            if (!lsb) {  // MAXIMAL: g = w*rank, l = p
-                base = w * r_max++;
-                kind = 1;
-            } else {     // NONE: g = EF[none_sizes_start+rank] + w*n_max, l = diff(none_pos) - p
-                base = S(ns + r_none) + maxblock + (S(np + r_none + 1) - S(np + r_none));
-                ++r_none;
-                kind = 2;
-            }
+            if (base >> 62) throw FormatError("bucket base does not fit 62 bits");
+            if (base > max_base) max_base = base;
+            // slope +1 (else -1) | colliding minimizer | base
+            e.set(b, kind == 1, kind == 0, base);
         }
-        if (base >> 62) throw FormatError("bucket base does not fit 62 bits");
-        if (base > max_base) max_base = base;
-        // bit 63: slope +1 (else -1), bit 62: colliding minimizer
-        e[b] = (uint64_t(kind == 1) << 63) | (uint64_t(kind == 0) << 62) | base;
-    }
-    for (uint64_t i = 0; i < free_slots.size(); ++i) {
-        if (free_slots[i] >= D) throw FormatError("single_phf: free slot outside [0, num_keys)");
-        e[D + i] = e[free_slots[i]];
-    }
-    img_.buckets.n = T;
-    // 32-bit entries whenever every base fits 30 bits; LPHB_FORCE_WIDE_BUCKETS=1 (test hook) keeps the
-    // 64-bit form, which only indexes of >= 2^30 k-mers would otherwise exercise
+        slice_max[slice] = max_base;
+    });
+    uint64_t max_base = 0;
+    for (uint64_t v : slice_max) max_base = v > max_base ? v : max_base;
+    finish_buckets(e, D, max_base, free_slots);
+}
+
+// The bucket table is written straight into the arena (at config-3 scale it is 3.3 GB: no temporary copy).
+// 32-bit entries when every base is sure to fit 30 bits - every base is a code of the function plus at
+// most k, so nkmers decides - else 64-bit; LPHB_FORCE_WIDE_BUCKETS=1 (test hook) keeps the 64-bit form, which
+// only indexes of about 2^30 k-mers or more would otherwise exercise.
+ImageBuilder::BucketWriter ImageBuilder::begin_buckets(uint64_t T) {
     const char* fw = getenv("LPHB_FORCE_WIDE_BUCKETS");
     const bool force_wide = fw && fw[0] && fw[0] != '0';
-    if (max_base < (1ull << 30) && !force_wide) {
-        std::vector<uint32_t> e32(T);
-        for (uint64_t b = 0; b < T; ++b)
-            e32[b] = uint32_t(e[b] >> 62) << 30 | uint32_t(e[b] & 0x3FFFFFFFull);  // same two flag bits on top
-        img_.buckets.wide = 0;
-        img_.buckets.entries = append(e32.data(), T, 8);
-    } else {
-        img_.buckets.wide = 1;
-        img_.buckets.entries = append(e.data(), T, 4);
-    }
+    BucketWriter wtr;
+    wtr.wide = force_wide || img_.nkmers + 256 >= (1ull << 30);
+    const uint64_t off = (arena_.size() + 255) & ~uint64_t(255);
+    arena_.resize(off + (wtr.wide ? (T + 4) * 8 : (T + 8) * 4), 0);
+    wtr.p = arena_.data() + off;
+    img_.buckets.n = T;
+    img_.buckets.wide = wtr.wide ? 1 : 0;
+    img_.buckets.entries = reinterpret_cast<const void*>(uintptr_t(off));
+    return wtr;
+}
+
+// free slots repeat the word of the key position they map to
+void ImageBuilder::finish_buckets(BucketWriter& e, uint64_t D, uint64_t max_base, std::vector<uint32_t> const& free_slots) {
+    if (!e.wide && max_base >= (1ull << 30)) throw FormatError("bucket base beyond the number of k-mers");
+    parallel_for(free_slots.size(), 1 << 16, [&](uint64_t i0, uint64_t i1, unsigned) {
+        for (uint64_t i = i0; i < i1; ++i) {
+            if (free_slots[i] >= D) throw FormatError("single_phf: free slot outside [0, num_keys)");
+            e.copy(D + i, free_slots[i]);
+        }
+    });
 }
 
 void reciprocal64(uint64_t d, uint32_t out[2]) {
@@ -239,18 +328,20 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
     for (uint64_t i = 0; i < fd.size; ++i) hp[i] = murmur64_host(fd.get(i), out.seed);
     for (uint64_t i = 0; i < bd.size; ++i) hp[fd.size + i] = murmur64_host(bd.get(i), out.seed);
     std::vector<uint64_t> per_bucket(nbuckets);
-    for (uint64_t b = 0; b < nbuckets; ++b) {
-        uint64_t r;
-        if (b < fr.size) {
-            r = fr.get(b);
-            if (r >= fd.size) throw FormatError("pilot rank outside dictionary");
-        } else {
-            r = br.get(b - fr.size);
-            if (r >= bd.size) throw FormatError("pilot rank outside dictionary");
-            r += fd.size;
+    parallel_for(nbuckets, 1 << 16, [&](uint64_t b0, uint64_t b1, unsigned) {
+        for (uint64_t b = b0; b < b1; ++b) {
+            uint64_t r;
+            if (b < fr.size) {
+                r = fr.get(b);
+                if (r >= fd.size) throw FormatError("pilot rank outside dictionary");
+            } else {
+                r = br.get(b - fr.size);
+                if (r >= bd.size) throw FormatError("pilot rank outside dictionary");
+                r += fd.size;
+            }
+            per_bucket[b] = hp[r];
         }
-        per_bucket[b] = hp[r];
-    }
+    });
     out.pilot_hash = append(per_bucket.data(), nbuckets, 2);
     // 64-bit PTHash hashes cap num_keys at 2^30 (hasher.hpp:27-31), so table_size = num_keys/alpha
     // stays below 2^31, which the device-side exact modulo relies on
@@ -264,10 +355,12 @@ void ImageBuilder::read_phf(Cursor& c, DevPhf& out) {
     if (free_vals.size() != out.table_size - out.num_keys)
         throw FormatError("single_phf: free-slot count mismatch");
     std::vector<uint32_t> f32(free_vals.size());
-    for (size_t i = 0; i < free_vals.size(); ++i) {
-        if (free_vals[i] >= out.table_size) throw FormatError("single_phf: free slot outside the table");
-        f32[i] = uint32_t(free_vals[i]);
-    }
+    parallel_for(free_vals.size(), 1 << 16, [&](uint64_t i0, uint64_t i1, unsigned) {
+        for (uint64_t i = i0; i < i1; ++i) {
+            if (free_vals[i] >= out.table_size) throw FormatError("single_phf: free slot outside the table");
+            f32[i] = uint32_t(free_vals[i]);
+        }
+    });
     out.free32 = append(f32.data(), f32.size(), 4);
     last_free_ = std::move(f32);
 }
@@ -304,6 +397,56 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
           img_.none_pos_start < sp.size()))
         throw FormatError("inconsistent sizes_and_positions partition");
     build_buckets(root, left_right, max_none, sp, mo_free);
+    fallback_keys_ = img_.fallback.num_keys;
+    file_bytes_ = n;
+    arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
+}
+
+void ImageBuilder::parse_alt(const uint8_t* data, uint64_t n, int kmer_bits) {
+    if (kmer_bits != 64 && kmer_bits != 128) throw FormatError("kmer_bits must be 64 or 128");
+    arena_.clear();
+    img_ = DevImage{};
+    Cursor c{data, data + n};
+    img_.k = c.pod<uint8_t>();
+    img_.m = c.pod<uint8_t>();
+    img_.kmer_bits = uint32_t(kmer_bits);
+    img_.mm_seed = c.pod<uint64_t>();
+    img_.nkmers = c.pod<uint64_t>();
+    img_.distinct_minimizers = c.pod<uint64_t>();
+    const uint64_t main_kmers = c.pod<uint64_t>();  // num_kmers_in_main_index
+    if (img_.m == 0 || img_.m > 31 || img_.k < img_.m || img_.k > uint32_t(kmer_bits / 2 - 1))
+        throw FormatError("k/m out of range for this kmer_t");
+    img_.w = img_.k - img_.m + 1;
+    read_phf(c, img_.minimizer_order);
+    std::vector<uint32_t> mo_free = std::move(last_free_);
+    std::vector<uint64_t> positions = read_ef(c), sizes = read_ef(c);
+    read_phf(c, img_.fallback);
+    if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
+    const uint64_t D = img_.distinct_minimizers;
+    if (img_.minimizer_order.num_keys != D || positions.size() != D + 1 || sizes.size() != D + 1)
+        throw FormatError("inconsistent minimizer counts");
+    img_.collision_base = main_kmers;  // unpartitioned_mphf.cpp:198
+    // one word per bucket: hval(k-mer) = base - p, base = sizes[i] + positions.diff(i)
+    // (unpartitioned_mphf.cpp:193-203); size 0 = colliding minimizer
+    BucketWriter e = begin_buckets(D + mo_free.size());
+    std::vector<uint64_t> slice_max(64, 0);
+    parallel_for(D, 1 << 16, [&](uint64_t b0, uint64_t b1, unsigned slice) {
+        uint64_t max_base = 0;
+        for (uint64_t b = b0; b < b1; ++b) {
+            if (sizes[b + 1] == sizes[b]) {
+                e.set(b, false, true, 0);
+            } else {
+                const uint64_t base = sizes[b] + (positions[b + 1] - positions[b]);
+                if (base >> 62) throw FormatError("bucket base does not fit 62 bits");
+                if (base > max_base) max_base = base;
+                e.set(b, false, false, base);  // slope -1
+            }
+        }
+        slice_max[slice] = max_base;
+    });
+    uint64_t max_base = 0;
+    for (uint64_t v : slice_max) max_base = v > max_base ? v : max_base;
+    finish_buckets(e, D, max_base, mo_free);
     fallback_keys_ = img_.fallback.num_keys;
     file_bytes_ = n;
     arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);

@@ -29,6 +29,13 @@ class ImageBuilder {
 public:
     // Parses `data[0..n)`; throws FormatError.  After this, image() holds offsets-as-pointers.
     void parse(const uint8_t* data, uint64_t n, int kmer_bits);
+    // The same for a serialized lphash::mphf_alt (the unpartitioned variant, build-u / query-u):
+    //   u8 k, u8 m, u64 mm_seed, nkmers, distinct_minimizers, num_kmers_in_main_index
+    //   single_phf minimizer_order, ef_sequence positions, ef_sequence sizes, single_phf fallback_kmer_order
+    //   (ref include/unpartitioned_mphf.hpp:198-210).  Its query (ref src/unpartitioned_mphf.cpp:191-206:
+    //   hval = sizes[i] + positions.diff(i) - p, or num_kmers_in_main_index + fallback(kmer) when the size is 0)
+    //   fits the same per-bucket word, so the device image and every kernel are shared with the partitioned form.
+    void parse_alt(const uint8_t* data, uint64_t n, int kmer_bits);
     std::vector<uint8_t> const& arena() const { return arena_; }
     // Returns the image with every pointer rebased onto `device_base`.
     DevImage rebased(const void* device_base) const;
@@ -49,6 +56,21 @@ private:
     };
     Bits read_bits(Cursor& c);
     void read_phf(Cursor& c, DevPhf& out);
+    // the bucket table under construction, inside the arena (flag bits on top of the base: device_image.h)
+    struct BucketWriter {
+        uint8_t* p = nullptr;
+        bool wide = false;
+        void set(uint64_t i, bool slope_up, bool colliding, uint64_t base) {
+            if (wide) reinterpret_cast<uint64_t*>(p)[i] = (uint64_t(slope_up) << 63) | (uint64_t(colliding) << 62) | base;
+            else reinterpret_cast<uint32_t*>(p)[i] = (uint32_t(slope_up) << 31) | (uint32_t(colliding) << 30) | uint32_t(base & 0x3FFFFFFFu);
+        }
+        void copy(uint64_t to, uint64_t from) {
+            if (wide) reinterpret_cast<uint64_t*>(p)[to] = reinterpret_cast<uint64_t*>(p)[from];
+            else reinterpret_cast<uint32_t*>(p)[to] = reinterpret_cast<uint32_t*>(p)[from];
+        }
+    };
+    BucketWriter begin_buckets(uint64_t T);
+    void finish_buckets(BucketWriter& e, uint64_t D, uint64_t max_base, std::vector<uint32_t> const& free_slots);
     void build_buckets(Bits const& root, Bits const& left_right, Bits const& max_none,
                        std::vector<uint64_t> const& sp, std::vector<uint32_t> const& free_slots);
 

@@ -22,7 +22,7 @@ fi
 mkdir -p "$OUT"
 # -DNDEBUG: the reference builds as CMake "Release" by default (CMakeLists.txt:5-7), i.e. with its asserts off
 CXXFLAGS="-std=c++17 -O3 -DNDEBUG -march=x86-64-v3 -mbmi2 -msse4.2 -pthread -include memory -w -fPIC"
-SRCS="src/constants.cpp src/quartet_wtree.cpp src/minimizer.cpp src/partitioned_mphf.cpp src/mphf_utils.cpp"
+SRCS="src/constants.cpp src/quartet_wtree.cpp src/minimizer.cpp src/partitioned_mphf.cpp src/unpartitioned_mphf.cpp src/mphf_utils.cpp"
 build_flavour() {
   local bits="$1" type="$2"
   local tmp; tmp="$(mktemp -d)"
@@ -32,7 +32,7 @@ build_flavour() {
   ln -s "$REF/external" "$tmp/external"
   echo "typedef $type kmer_t;" > "$tmp/include/compile_constants.tpd"
   ( cd "$tmp" && g++ $CXXFLAGS -shared -I"$tmp" -o "$OUT/libref$bits.so" "$HERE/ref_harness.cpp" $SRCS -lz ) &
-  ( cd "$tmp" && g++ $CXXFLAGS -o "$OUT/lphash$bits" src/lphash.cpp $SRCS src/unpartitioned_mphf.cpp src/parser_build.cpp -lz ) &
+  ( cd "$tmp" && g++ $CXXFLAGS -o "$OUT/lphash$bits" src/lphash.cpp $SRCS src/parser_build.cpp -lz ) &
   wait
 }
 build_flavour 64 uint64_t

@@ -73,6 +73,16 @@ def lib(bits: int) -> C.CDLL:
     L.ref_scan_batch.restype = C.c_double
     L.ref_scan_batch.argtypes = [p, p, u64, C.c_uint32, C.c_uint32, u64, C.c_int, C.c_char_p,
                                  C.POINTER(u64), C.POINTER(u64)]
+    L.ref_build_alt.restype = C.c_int
+    L.ref_build_alt.argtypes = [C.c_char_p, C.c_int, C.c_int, u64, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                C.c_char_p, u64]
+    L.ref_load_alt.restype = p
+    L.ref_load_alt.argtypes = [C.c_char_p]
+    L.ref_free_alt.argtypes = [p]
+    L.ref_kmer_count_alt.restype = u64
+    L.ref_kmer_count_alt.argtypes = [p]
+    L.ref_query_alt.restype = C.c_int64
+    L.ref_query_alt.argtypes = [p, C.c_char_p, u64, C.c_int, p, u64]
     assert L.ref_kmer_bits() == bits
     _libs[bits] = L
     return L
@@ -93,6 +103,47 @@ def build(input_path: str, k: int, m: int, output: str, *, bits: int = 64, seed:
     if rc != 0:
         raise RuntimeError("reference build failed: " + L.ref_last_error().decode())
     return buf.value.decode().strip()
+
+
+def build_alt(input_path: str, k: int, m: int, output: str, *, bits: int = 64, seed: int = 42,
+              c: float = 3.0, threads: int = 1, max_memory_gb: int = 8, tmp_dir: str | None = None) -> str:
+    """build-u through the reference's own mphf_alt::build + essentials::save; returns its CSV line."""
+    L = lib(bits)
+    tmp = tmp_dir or _tmp()
+    buf = C.create_string_buffer(4096)
+    rc = L.ref_build_alt(input_path.encode(), k, m, seed, c, threads, max_memory_gb, tmp.encode(),
+                         output.encode(), buf, 4096)
+    if rc != 0:
+        raise RuntimeError("reference build-u failed: " + L.ref_last_error().decode())
+    return buf.value.decode().strip()
+
+
+class RefMphfAlt:
+    """A loaded reference `lphash::mphf_alt` (the unpartitioned variant, build-u / query-u)."""
+
+    def __init__(self, path: str, bits: int = 64):
+        self.L = lib(bits)
+        self.h = self.L.ref_load_alt(path.encode())
+        if not self.h:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.ref_free_alt(self.h)
+            self.h = None
+
+    @property
+    def kmer_count(self) -> int:
+        return self.L.ref_kmer_count_alt(self.h)
+
+    def query(self, contig: bytes, streaming: bool = True) -> np.ndarray:
+        cap = max(len(contig), 1)
+        out = np.empty(cap, dtype=np.uint64)
+        n = self.L.ref_query_alt(self.h, contig, len(contig), 1 if streaming else 0, out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        assert n <= cap
+        return out[:n].copy()
 
 
 class RefMphf:

@@ -11,6 +11,7 @@
 //   lphash::minimizer::from_string          include/minimizer.hpp:11-170
 //   lphash::minimizer::classify             src/minimizer.cpp:5-50
 //   lphash::minimizer::get_colliding_kmers  include/minimizer.hpp:172-319
+//   lphash::mphf_alt::build / operator()    src/unpartitioned_mphf.cpp:31-140, include/unpartitioned_mphf.hpp:72-192
 //   essentials::save / load                 pthash/external/essentials/include/essentials.hpp:595-607
 //
 // Users: tests/ (to pin the CPU restatement in oracle/lphash_oracle.cpp and to generate the
@@ -27,6 +28,7 @@
 #include <vector>
 
 #include "include/partitioned_mphf.hpp"
+#include "include/unpartitioned_mphf.hpp"
 #include "include/minimizer.hpp"
 
 using lphash::kmer_t;
@@ -72,6 +74,56 @@ int ref_build(const char* input, int k, int m, uint64_t seed, double c, int thre
             csv_out[csv_cap - 1] = 0;
         }
         return 0;
+    } catch (std::exception const& e) { return fail(e); }
+}
+
+// build-u / query-u: the unpartitioned variant (lphash::mphf_alt), same calling conventions
+int ref_build_alt(const char* input, int k, int m, uint64_t seed, double c, int threads,
+                  int max_memory_gb, const char* tmp_dir, const char* output, char* csv_out, uint64_t csv_cap) {
+    try {
+        lphash::configuration config;
+        config.input_filename = input;
+        config.output_filename = output ? output : "";
+        config.k = k;
+        config.m = m;
+        config.mm_seed = seed;
+        config.c = c;
+        config.num_threads = threads;
+        config.max_memory = max_memory_gb;
+        config.tmp_dirname = tmp_dir ? tmp_dir : ".";
+        config.check = false;
+        config.verbose = false;
+        lphash::mphf_alt f;
+        std::ostringstream csv;
+        f.build(config, csv);
+        if (output && output[0]) essentials::save(f, output);
+        if (csv_out && csv_cap) {
+            std::string s = csv.str();
+            std::strncpy(csv_out, s.c_str(), csv_cap - 1);
+            csv_out[csv_cap - 1] = 0;
+        }
+        return 0;
+    } catch (std::exception const& e) { return fail(e); }
+}
+void* ref_load_alt(const char* path) {
+    try {
+        auto* f = new lphash::mphf_alt();
+        essentials::load(*f, path);
+        return f;
+    } catch (std::exception const& e) {
+        fail(e);
+        return nullptr;
+    }
+}
+void ref_free_alt(void* h) { delete static_cast<lphash::mphf_alt*>(h); }
+uint64_t ref_kmer_count_alt(void* h) { return static_cast<lphash::mphf_alt*>(h)->get_kmer_count(); }
+int64_t ref_query_alt(void* h, const char* contig, uint64_t len, int streaming, uint64_t* out, uint64_t cap) {
+    try {
+        auto const& f = *static_cast<lphash::mphf_alt const*>(h);
+        auto codes = f(contig, len, streaming != 0);
+        uint64_t n = codes.size() < cap ? codes.size() : cap;
+        if (out && n) std::memcpy(out, codes.data(), n * sizeof(uint64_t));
+        return int64_t(codes.size());
     } catch (std::exception const& e) { return fail(e); }
 }
 

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import GOLDEN_DIR, ROOT, load_golden
 from lphash_b200 import api
 
 HEADER = os.path.join(ROOT, "include", "lphash_b200.h")
@@ -114,3 +114,24 @@ def test_expand_runs_is_host_only_and_exact():
     n = C.c_uint64(0)
     rc = api.lib().lphb_expand_runs(runs.ctypes.data, n_runs, small.ctypes.data, 3, C.byref(n), 1)
     assert rc == api.E_CAPACITY and n.value == len(want)
+
+
+def test_unpartitioned_images_parse_and_cross_loading_is_rejected():
+    """The host-side parser of the mphf_alt format runs before any CUDA call: on a box without a GPU a good
+    image gets as far as LPHB_E_CUDA, a partitioned image fed to the unpartitioned loader (or truncated) stops
+    at LPHB_E_FORMAT."""
+    import ctypes as C
+    L = api.lib()
+    h = C.c_void_p()
+    alt = os.path.join(GOLDEN_DIR, "alt_k31_m20_u64.lph")
+    rc = L.lphb_mphf_alt_load_file(alt.encode(), 64, 0, C.byref(h))
+    assert rc in (0, api.E_CUDA), L.lphb_last_error()
+    if rc == 0:
+        L.lphb_mphf_free(h)
+    part = os.path.join(GOLDEN_DIR, "k31_m20_u64.lph")
+    assert L.lphb_mphf_alt_load_file(part.encode(), 64, 0, C.byref(h)) == api.E_FORMAT
+    assert L.lphb_mphf_load_file(alt.encode(), 64, 0, C.byref(h)) == api.E_FORMAT
+    img = open(alt, "rb").read()
+    for cut in (10, 58, len(img) // 2, len(img) - 1):
+        buf = (C.c_char * cut).from_buffer_copy(img[:cut])
+        assert L.lphb_mphf_alt_load_memory(C.addressof(buf), cut, 64, 0, C.byref(h)) == api.E_FORMAT

@@ -113,13 +113,13 @@ def exe(tmp_path_factory):
     d = tmp_path_factory.mktemp("fastx")
     out = str(d / "fastx_check")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-DLPHASH_B200_WITH_ZLIB",
-                           "-I", os.path.join(ROOT, "include"), SRC, "-o", out, "-lz"])
+                           "-I", os.path.join(ROOT, "include"), SRC, "-o", out, "-lz", "-pthread"])
     return out
 
 
-def run(exe, path, tmp):
+def run(exe, path, tmp, chunk=None):
     outp = os.path.join(tmp, "out.bin")
-    subprocess.check_call([exe, path, outp])
+    subprocess.check_call([exe, path, outp] + ([str(chunk)] if chunk else []))
     raw = open(outp, "rb").read()
     n = int(np.frombuffer(raw, dtype="<u8", count=1)[0])
     off = np.frombuffer(raw, dtype="<u8", count=n + 1, offset=8)
@@ -133,6 +133,17 @@ def test_matches_kseq_grammar(exe, tmp_path, name):
     path = str(tmp_path / (name + ".txt"))
     open(path, "wb").write(data)
     assert run(exe, path, str(tmp_path)) == kseq_records(data)
+
+
+@pytest.mark.parametrize("chunk", [16, 23, 64, 4096])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_streaming_ingest_matches_kseq_grammar(exe, tmp_path, name, chunk):
+    """stream_file: the text arrives in chunks (a record straddling a chunk end is held back and re-parsed with the
+    next chunk; a FASTQ quality string cut by the chunk is not mistaken for a malformed one)."""
+    data = CASES[name]
+    path = str(tmp_path / (name + ".txt"))
+    open(path, "wb").write(data)
+    assert run(exe, path, str(tmp_path), chunk) == kseq_records(data)
 
 
 def test_gzip_and_large_random(exe, tmp_path):
@@ -155,6 +166,8 @@ def test_gzip_and_large_random(exe, tmp_path):
     want = kseq_records(data)
     assert len(got) == len(want) == 3000
     assert got == want
+    for chunk in (97, 1000, 65536):  # the same through the streaming ingest (gz inflated chunk by chunk)
+        assert run(exe, path, str(tmp_path), chunk) == want
 
 
 @pytest.mark.parametrize("name", ["fasta_multiline", "fasta_crlf", "fastq_4line"])
@@ -231,7 +244,7 @@ def test_example_query_driver_end_to_end(tmp_path, name):
     libdir = os.path.join(ROOT, "lphash_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-DLPHASH_B200_WITH_ZLIB", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "examples", "lphb_query.cpp"), "-o", exe, "-L", libdir,
-                           "-llphash_b200", f"-Wl,-rpath,{libdir}", "-lz"])
+                           "-llphash_b200", f"-Wl,-rpath,{libdir}", "-lz", "-pthread"])
     keep, parts = [], []
     for i, c in enumerate(g.contigs()):
         if any(b in c for b in (b"\n", b"\r", b">", b"@", b"+", b"\0")):
@@ -243,6 +256,11 @@ def test_example_query_driver_end_to_end(tmp_path, name):
         f.write(b"".join(parts))
     off = g.q_code_offsets
     want = np.concatenate([g.q_codes[int(off[i]):int(off[i + 1])] for i in keep])
+    fold = fnv_fold(want)
     out = subprocess.check_output([exe, g.lph, str(g.bits), path], text=True).strip().split(",")
     assert int(out[2]) == len(want)
-    assert int(out[5], 16) == fnv_fold(want)
+    assert int(out[5], 16) == fold
+    # tiny chunks (many batches, records held back across chunk ends) and the run-length output form
+    for extra in (["0", "0"], ["0", "1", "runs"]):
+        out = subprocess.check_output([exe, g.lph, str(g.bits), path] + extra, text=True).strip().split(",")
+        assert int(out[2]) == len(want) and int(out[5], 16) == fold, extra
