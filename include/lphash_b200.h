@@ -194,6 +194,49 @@ int lphb_scan_classify(int device, uint32_t k, uint32_t m, uint64_t seed, const 
                        uint64_t triplets_capacity, uint64_t* n_triplets, uint64_t* ids,
                        uint64_t ids_capacity, uint64_t* n_ids, uint64_t* n_kmers);
 
+/* ---- build-p Part 3: the inverted index --------------------------------------------------------
+ * Replaces the loop that re-keys every triplet by minimizer_order(itself) and sorts the result
+ * (src/partitioned_mphf.cpp:92-106) and mphf::build_inverted_index (src/partitioned_mphf.cpp:163-268):
+ * type of every distinct minimizer, the quartet wavelet tree with its rank directories
+ * (src/quartet_wtree.cpp:13-53, include/rs_bit_vector.hpp:120-156), the four size / position lists and
+ * the Elias-Fano encoding of their prefix sums (include/ef_sequence.hpp:36-75) with its darray1 select
+ * index (pthash/include/encoders/darray.hpp:13-48).
+ * minimizer_order = the serialized pthash::single_phf built on the distinct minimizers (the bytes
+ * essentials::save writes for it; PTHash construction itself stays with the caller); triplets = the
+ * packed 10-byte mm_triplet_t of lphb_classify, one per distinct minimizer, in any order.
+ * out receives, byte for byte as in the `.lph` file, the image of `wtree` followed by the image of
+ * `sizes_and_positions` (include/partitioned_mphf.hpp:213-214); info the four counters stored in front
+ * of them.  lphb_inverted_index_bound(n) is a capacity that always suffices; *out_bytes is also set
+ * when returning LPHB_E_CAPACITY.  LPHB_E_ARG if minimizer_order is not a bijection of the triplets'
+ * minimizers onto [0, n_triplets).                                                                   */
+typedef struct lphb_inverted_index {
+    uint64_t n_maximal, right_coll_sizes_start, none_sizes_start, none_pos_start; /* include/partitioned_mphf.hpp:208-211 */
+    uint64_t colliding_minimizers; /* triplets of size 0 */
+    uint64_t universe;             /* last prefix sum (src/partitioned_mphf.cpp:267) */
+    uint64_t wtree_bytes, ef_bytes; /* the two images inside out */
+    double device_ms;              /* CUDA-event time of the kernels, copies excluded */
+} lphb_inverted_index;
+uint64_t lphb_inverted_index_bound(uint64_t n_triplets);
+int lphb_build_inverted_index(int device, uint32_t k, uint32_t m, const void* minimizer_order,
+                              uint64_t minimizer_order_bytes, const void* triplets, uint64_t n_triplets,
+                              void* out, uint64_t out_capacity, uint64_t* out_bytes,
+                              lphb_inverted_index* info);
+
+/* ---- the `.lph` writer (host only) ------------------------------------------------------------
+ * lphb_lph_assemble lays out a complete serialized lphash::mphf in the visitor order of
+ * include/partitioned_mphf.hpp:204-219 - what essentials::save(hf, file) writes (src/build.cpp:52) -
+ * from the header fields, the two serialized single_phf objects (built by PTHash on the caller's side)
+ * and the index body of lphb_build_inverted_index.  The result loads with the reference's
+ * essentials::load and with lphb_mphf_load_memory.
+ * lphb_lph_sections reports where the parts of an existing image start: minimizer_order, the wavelet
+ * tree (alt: positions), sizes_and_positions (alt: sizes), fallback_kmer_order, end of the image.   */
+int lphb_lph_assemble(uint32_t k, uint32_t m, uint64_t mm_seed, uint64_t nkmers, uint64_t distinct_minimizers,
+                      const lphb_inverted_index* index, const void* minimizer_order,
+                      uint64_t minimizer_order_bytes, const void* index_body, uint64_t index_body_bytes,
+                      const void* fallback_kmer_order, uint64_t fallback_bytes, void* out,
+                      uint64_t out_capacity, uint64_t* out_bytes);
+int lphb_lph_sections(const void* image, uint64_t nbytes, int kmer_bits, int alt, uint64_t sections[5]);
+
 /* ---- build-p Part 4: k-mers of colliding minimizers -----------------------------------------
  * Replaces the loop over minimizer::get_colliding_kmers (include/minimizer.hpp:172-319; caller
  * src/partitioned_mphf.cpp:120-129).  ids = ascending minimizer-occurrence ids (classify's second

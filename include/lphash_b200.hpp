@@ -26,6 +26,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -186,6 +187,42 @@ struct memory_saver {
         } else {
             for (auto& v : vec) visit(v);
         }
+    }
+};
+
+// The inverse: essentials' loader protocol (essentials.hpp:280-324) over a byte image in memory.
+struct memory_loader {
+    const unsigned char* p;
+    const unsigned char* end;
+    memory_loader(const void* image, size_t nbytes)
+        : p(static_cast<const unsigned char*>(image)), end(static_cast<const unsigned char*>(image) + nbytes) {}
+    template <typename T>
+    void visit(T& val) {
+        if constexpr (std::is_pod<T>::value) {
+            take(&val, sizeof(T));
+        } else {
+            val.visit(*this);
+        }
+    }
+    template <typename T, typename Allocator>
+    void visit(std::vector<T, Allocator>& vec) {
+        size_t n = 0;
+        visit(n);
+        if constexpr (std::is_pod<T>::value) {
+            if (n > size_t(end - p) / sizeof(T)) throw std::runtime_error("lphash_b200: truncated image");
+            vec.resize(n);
+            take(vec.data(), n * sizeof(T));
+        } else {
+            vec.resize(n);
+            for (auto& v : vec) visit(v);
+        }
+    }
+
+private:
+    void take(void* dst, size_t n) {
+        if (size_t(end - p) < n) throw std::runtime_error("lphash_b200: truncated image");
+        if (n) std::memcpy(dst, p, n);
+        p += n;
     }
 };
 

@@ -33,7 +33,7 @@ build_flavour() {
       g++ $CXXFLAGS -DLPHASH_B200_REFERENCE_TU -Dmphf=mphf_reference -I"$ROOT/include" -c "$f" -o "$(basename "$f" .cpp).o" &
     done
     # the driver, unmodified: its `mphf` is the GPU-backed class of the shadow header
-    g++ $CXXFLAGS -DLPHASH_B200_KMER_BITS="$bits" -I"$ROOT/include" -c src/lphash.cpp -o lphash.o &
+    g++ $CXXFLAGS -DLPHASH_B200_KMER_BITS="$bits" -DLPHASH_B200_WITH_ZLIB -I"$ROOT/include" -c src/lphash.cpp -o lphash.o &
     wait
     g++ -o "$OUT/lphash_gpu$bits" lphash.o constants.o quartet_wtree.o minimizer.o partitioned_mphf.o mphf_utils.o \
         unpartitioned_mphf.o parser_build.o -L"$ROOT/lphash_b200" -llphash_b200 -Wl,-rpath,'$ORIGIN/../../lphash_b200' -lz -pthread )

@@ -42,6 +42,12 @@ class Info(C.Structure):
                 ("load_host_ms", C.c_double), ("load_h2d_ms", C.c_double)]
 
 
+class InvertedIndex(C.Structure):
+    _fields_ = [("n_maximal", C.c_uint64), ("right_coll_sizes_start", C.c_uint64), ("none_sizes_start", C.c_uint64),
+                ("none_pos_start", C.c_uint64), ("colliding_minimizers", C.c_uint64), ("universe", C.c_uint64),
+                ("wtree_bytes", C.c_uint64), ("ef_bytes", C.c_uint64), ("device_ms", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("dirty_contigs", C.c_uint64), ("kernel_ms", C.c_double)]
@@ -54,7 +60,8 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_host_alloc", "lphb_host_free", "lphb_mphf_stats", "lphb_scan_release", "lphb_classify", "lphb_scan_classify",
            "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags",
            "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming",
-           "lphb_mphf_alt_load_file", "lphb_mphf_alt_load_memory"]
+           "lphb_mphf_alt_load_file", "lphb_mphf_alt_load_memory", "lphb_inverted_index_bound",
+           "lphb_build_inverted_index", "lphb_lph_assemble", "lphb_lph_sections"]
 
 _lib = None
 
@@ -97,6 +104,13 @@ def lib() -> C.CDLL:
                                      C.POINTER(u64), p, u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_copy_to_host.argtypes = [i32, p, p, u64]
     L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
+    L.lphb_inverted_index_bound.argtypes = [u64]
+    L.lphb_inverted_index_bound.restype = u64
+    L.lphb_build_inverted_index.argtypes = [i32, C.c_uint32, C.c_uint32, p, u64, p, u64, p, u64, C.POINTER(u64),
+                                            C.POINTER(InvertedIndex)]
+    L.lphb_lph_assemble.argtypes = [C.c_uint32, C.c_uint32, u64, u64, u64, C.POINTER(InvertedIndex), p, u64, p, u64, p,
+                                    u64, p, u64, C.POINTER(u64)]
+    L.lphb_lph_sections.argtypes = [p, u64, i32, i32, C.POINTER(u64)]
     L.lphb_host_free.argtypes = [p]
     for name in EXPORTS:
         if getattr(L, name).restype is C.c_int:
@@ -332,3 +346,41 @@ def colliding_kmers(bases, offsets, k: int, m: int, ids, seed: int = 42, kmer_bi
                                       C.byref(mm), ids.ctypes.data, len(ids), kmer_bits,
                                       out.ctypes.data, cap, C.byref(nk)))
     return out[: nk.value]
+
+
+def build_inverted_index(k: int, m: int, minimizer_order: bytes, triplets, device: int = 0, capacity: int | None = None):
+    """build-p Part 3 (re-key by minimizer_order + mphf::build_inverted_index, /root/reference/src/
+    partitioned_mphf.cpp:92-106, 163-268).  minimizer_order = serialized single_phf; triplets = TRIPLET_DTYPE array.
+    Returns (InvertedIndex, body bytes = image of wtree + image of sizes_and_positions)."""
+    trip = np.ascontiguousarray(triplets, dtype=TRIPLET_DTYPE)
+    phf = np.frombuffer(minimizer_order, dtype=np.uint8)
+    cap = lib().lphb_inverted_index_bound(len(trip)) if capacity is None else capacity
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    info = InvertedIndex()
+    nb = C.c_uint64(0)
+    _check(lib().lphb_build_inverted_index(device, k, m, phf.ctypes.data, len(phf), trip.ctypes.data, len(trip),
+                                           out.ctypes.data, cap, C.byref(nb), C.byref(info)))
+    return info, out[: nb.value].tobytes()
+
+
+def lph_sections(image: bytes, kmer_bits: int = 64, alt: bool = False) -> list[int]:
+    """Start of minimizer_order, of the wavelet tree (alt: positions), of sizes_and_positions (alt: sizes), of
+    fallback_kmer_order, and the end of a serialized index.  Host only."""
+    buf = np.frombuffer(image, dtype=np.uint8)
+    sec = (C.c_uint64 * 5)()
+    _check(lib().lphb_lph_sections(buf.ctypes.data, len(buf), kmer_bits, int(alt), sec))
+    return [int(v) for v in sec]
+
+
+def lph_assemble(k: int, m: int, mm_seed: int, nkmers: int, distinct_minimizers: int, index: InvertedIndex,
+                 minimizer_order: bytes, index_body: bytes, fallback_kmer_order: bytes) -> bytes:
+    """A complete `.lph` image (what essentials::save writes, /root/reference/src/build.cpp:52) from its parts.  Host only."""
+    mo = np.frombuffer(minimizer_order, dtype=np.uint8)
+    body = np.frombuffer(index_body, dtype=np.uint8)
+    fb = np.frombuffer(fallback_kmer_order, dtype=np.uint8)
+    cap = 58 + len(mo) + len(body) + len(fb)
+    out = np.empty(cap, dtype=np.uint8)
+    nb = C.c_uint64(0)
+    _check(lib().lphb_lph_assemble(k, m, mm_seed, nkmers, distinct_minimizers, C.byref(index), mo.ctypes.data, len(mo),
+                                   body.ctypes.data, len(body), fb.ctypes.data, len(fb), out.ctypes.data, cap, C.byref(nb)))
+    return out[: nb.value].tobytes()

@@ -17,52 +17,22 @@
 #include <vector>
 
 #include "../../include/lphash_b200.h"
+#include "api_internal.h"
 #include "lph_image.h"
 #include "query_kernels.cuh"
 #include "scan_kernels.cuh"
 
 using namespace lphb;
 
+namespace lphb {
+std::string& last_error_slot() {
+    thread_local std::string err;
+    return err;
+}
+}  // namespace lphb
+
 namespace {
 
-thread_local std::string g_err;
-
-int fail(int code, std::string const& msg) {
-    g_err = msg;
-    return code;
-}
-
-struct CudaError {
-    cudaError_t e;
-    const char* what;
-};
-#define CK(expr)                                              \
-    do {                                                      \
-        cudaError_t e__ = (expr);                             \
-        if (e__ != cudaSuccess) throw CudaError{e__, #expr}; \
-    } while (0)
-
-// grow-only device / pinned buffers
-struct DevBuf {
-    void* p = nullptr;
-    uint64_t cap = 0;
-    void reserve(uint64_t bytes) {
-        if (bytes <= cap) return;
-        if (p) CK(cudaFree(p));
-        p = nullptr;
-        cap = 0;
-        uint64_t want = bytes + bytes / 8 + 256;
-        CK(cudaMalloc(&p, want));
-        cap = want;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T>
-    T* as() const { return static_cast<T*>(p); }
-};
 
 struct Workspace {
     DevBuf bases, offsets, code_off, codes, dirty, status, tmp, aux0, aux1, aux2, aux3, codes2, tile;
@@ -169,34 +139,6 @@ struct lphb_mphf {
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        CK(cudaGetDevice(&prev));
-        if (prev != dev) CK(cudaSetDevice(dev));
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-template <class F>
-int guarded(F&& body) {
-    try {
-        return body();
-    } catch (CudaError const& e) {
-        cudaGetLastError();
-        return fail(LPHB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e.e) + " in " + e.what);
-    } catch (FormatError const& e) {
-        return fail(LPHB_E_FORMAT, e.what());
-    } catch (std::bad_alloc const&) {
-        return fail(LPHB_E_NOMEM, "out of host memory");
-    } catch (std::exception const& e) {
-        return fail(LPHB_E_ARG, e.what());
-    }
-}
-
 int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_mphf** out, bool alt = false) {
     if (!out) return fail(LPHB_E_ARG, "out is null");
     *out = nullptr;
@@ -301,7 +243,7 @@ void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
 
 extern "C" {
 
-const char* lphb_last_error(void) { return g_err.c_str(); }
+const char* lphb_last_error(void) { return last_error_slot().c_str(); }
 const char* lphb_version(void) { return "lphash_b200 0.1 (sm_100a)"; }
 
 int lphb_device_count(int* count) {

@@ -383,11 +383,16 @@ void ImageBuilder::parse(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (img_.m == 0 || img_.m > 31 || img_.k < img_.m || img_.k > uint32_t(kmer_bits / 2 - 1))
         throw FormatError("k/m out of range for this kmer_t");
     img_.w = img_.k - img_.m + 1;
+    sections_[0] = uint64_t(c.p - data);
     read_phf(c, img_.minimizer_order);
     std::vector<uint32_t> mo_free = std::move(last_free_);
+    sections_[1] = uint64_t(c.p - data);
     Bits root = read_bits(c), left_right = read_bits(c), max_none = read_bits(c);
+    sections_[2] = uint64_t(c.p - data);
     std::vector<uint64_t> sp = read_ef(c);
+    sections_[3] = uint64_t(c.p - data);
     read_phf(c, img_.fallback);
+    sections_[4] = uint64_t(c.p - data);
     if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
     if (img_.minimizer_order.num_keys != img_.distinct_minimizers ||
         root.nbits != img_.distinct_minimizers ||
@@ -417,10 +422,16 @@ void ImageBuilder::parse_alt(const uint8_t* data, uint64_t n, int kmer_bits) {
     if (img_.m == 0 || img_.m > 31 || img_.k < img_.m || img_.k > uint32_t(kmer_bits / 2 - 1))
         throw FormatError("k/m out of range for this kmer_t");
     img_.w = img_.k - img_.m + 1;
+    sections_[0] = uint64_t(c.p - data);
     read_phf(c, img_.minimizer_order);
     std::vector<uint32_t> mo_free = std::move(last_free_);
-    std::vector<uint64_t> positions = read_ef(c), sizes = read_ef(c);
+    sections_[1] = uint64_t(c.p - data);
+    std::vector<uint64_t> positions = read_ef(c);
+    sections_[2] = uint64_t(c.p - data);
+    std::vector<uint64_t> sizes = read_ef(c);
+    sections_[3] = uint64_t(c.p - data);
     read_phf(c, img_.fallback);
+    sections_[4] = uint64_t(c.p - data);
     if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
     const uint64_t D = img_.distinct_minimizers;
     if (img_.minimizer_order.num_keys != D || positions.size() != D + 1 || sizes.size() != D + 1)
@@ -448,6 +459,16 @@ void ImageBuilder::parse_alt(const uint8_t* data, uint64_t n, int kmer_bits) {
     for (uint64_t v : slice_max) max_base = v > max_base ? v : max_base;
     finish_buckets(e, D, max_base, mo_free);
     fallback_keys_ = img_.fallback.num_keys;
+    file_bytes_ = n;
+    arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
+}
+
+void ImageBuilder::parse_phf(const uint8_t* data, uint64_t n) {
+    arena_.clear();
+    img_ = DevImage{};
+    Cursor c{data, data + n};
+    read_phf(c, img_.minimizer_order);
+    if (c.p != c.end) throw FormatError("trailing bytes after the serialized single_phf");
     file_bytes_ = n;
     arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
 }

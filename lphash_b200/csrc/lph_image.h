@@ -36,6 +36,12 @@ public:
     //   hval = sizes[i] + positions.diff(i) - p, or num_kmers_in_main_index + fallback(kmer) when the size is 0)
     //   fits the same per-bucket word, so the device image and every kernel are shared with the partitioned form.
     void parse_alt(const uint8_t* data, uint64_t n, int kmer_bits);
+    // A serialized pthash::single_phf on its own (what build-p Part 3 evaluates, ref src/partitioned_mphf.cpp:
+    // 96-100): afterwards the image holds `minimizer_order` only, free slots included.
+    void parse_phf(const uint8_t* data, uint64_t n);
+    // Byte offsets inside the image parsed last: start of minimizer_order, of the wavelet tree (alt: positions),
+    // of sizes_and_positions (alt: sizes), of fallback_kmer_order, end of the image.
+    const uint64_t* sections() const { return sections_; }
     std::vector<uint8_t> const& arena() const { return arena_; }
     // Returns the image with every pointer rebased onto `device_base`.
     DevImage rebased(const void* device_base) const;
@@ -77,6 +83,7 @@ private:
     std::vector<uint8_t> arena_;
     DevImage img_{};
     uint64_t fallback_keys_ = 0, file_bytes_ = 0;
+    uint64_t sections_[5] = {0, 0, 0, 0, 0};
     std::vector<uint32_t> last_free_;  // free slots of the PHF parsed last
 };
 

@@ -725,6 +725,21 @@ u64 orc_minimizer_order(void* h, u64 mmer) {
     auto& f = *static_cast<orc::Mphf*>(h);
     return f.minimizer_order.position(orc::murmur64(mmer, f.minimizer_order.seed));
 }
+// minimizer_order(keys[i]) through a serialized single_phf on its own (build-p Part 3 re-keys the triplets with
+// it, ref src/partitioned_mphf.cpp:96-100)
+int orc_phf_positions(const unsigned char* phf, u64 nbytes, const u64* keys, u64 n, u64* out) {
+    try {
+        orc::Reader r{phf, phf + nbytes};
+        orc::SinglePhf f;
+        f.read(r);
+        if (r.p != r.end) throw std::runtime_error("trailing bytes after the single_phf");
+        for (u64 i = 0; i < n; ++i) out[i] = f.position(orc::murmur64(keys[i], f.seed));
+        return 0;
+    } catch (std::exception const& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 u64 orc_fallback_order(void* h, u64 lo, u64 hi) {
     return static_cast<orc::Mphf*>(h)->fallback_order((u128(hi) << 64) | lo);
 }

@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
     L.orc_fastmod.argtypes = [u64, u64]
     L.orc_minimizer_order.restype = u64
     L.orc_minimizer_order.argtypes = [p, u64]
+    L.orc_phf_positions.restype = C.c_int
+    L.orc_phf_positions.argtypes = [p, u64, p, u64, p]
     L.orc_fallback_order.restype = u64
     L.orc_fallback_order.argtypes = [p, u64, u64]
     L.orc_rank_of.argtypes = [p, u64, C.POINTER(C.c_int), C.POINTER(u64)]
@@ -146,6 +148,16 @@ class OracleMphf:
 
 def murmur64(v: int, seed: int) -> int:
     return lib().orc_murmur64(v, seed)
+
+
+def phf_positions(phf: bytes, keys: np.ndarray) -> np.ndarray:
+    """single_phf(keys[i]) for a serialized pthash::single_phf over u64 keys (minimizer_order on its own)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    buf = np.frombuffer(phf, dtype=np.uint8)
+    out = np.empty(len(keys), dtype=np.uint64)
+    if lib().orc_phf_positions(buf.ctypes.data, len(buf), keys.ctypes.data, len(keys), out.ctypes.data) != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    return out
 
 
 def fastmod(a: int, d: int) -> int:

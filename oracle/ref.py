@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 import tempfile
 
 import numpy as np
@@ -83,6 +84,10 @@ def lib(bits: int) -> C.CDLL:
     L.ref_kmer_count_alt.argtypes = [p]
     L.ref_query_alt.restype = C.c_int64
     L.ref_query_alt.argtypes = [p, C.c_char_p, u64, C.c_int, p, u64]
+    L.ref_build_minimizer_phf.restype = C.c_int
+    L.ref_build_minimizer_phf.argtypes = [p, u64, C.c_double, C.c_int, C.c_char_p, C.c_char_p]
+    L.ref_ef_sequence.restype = C.c_int
+    L.ref_ef_sequence.argtypes = [p, u64, u64, C.c_char_p]
     assert L.ref_kmer_bits() == bits
     _libs[bits] = L
     return L
@@ -263,3 +268,29 @@ def colliding_kmers(bases: np.ndarray, offsets: np.ndarray, k: int, m: int, ids:
     if n < 0:
         raise RuntimeError(L.ref_last_error().decode())
     return out[:n].copy()
+
+
+def build_minimizer_phf(keys: np.ndarray, c: float = 3.0, threads: int = 1) -> bytes:
+    """The serialized minimizer_order the reference builds on `keys` (src/partitioned_mphf.cpp:45-52, 147-153)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    d = _tmp()
+    try:
+        out = os.path.join(d, "phf.bin")
+        if lib(64).ref_build_minimizer_phf(keys.ctypes.data, len(keys), c, threads, d.encode(), out.encode()) != 0:
+            raise RuntimeError(lib(64).ref_last_error().decode())
+        return open(out, "rb").read()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def ef_sequence(values: np.ndarray, universe: int) -> bytes:
+    """essentials::save of ef_sequence::encode(values, n, universe) (include/ef_sequence.hpp:36-75)."""
+    values = np.ascontiguousarray(values, dtype=np.uint64)
+    d = _tmp()
+    try:
+        out = os.path.join(d, "ef.bin")
+        if lib(64).ref_ef_sequence(values.ctypes.data, len(values), universe, out.encode()) != 0:
+            raise RuntimeError(lib(64).ref_last_error().decode())
+        return open(out, "rb").read()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

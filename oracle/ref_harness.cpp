@@ -13,6 +13,8 @@
 //   lphash::minimizer::get_colliding_kmers  include/minimizer.hpp:172-319
 //   lphash::mphf_alt::build / operator()    src/unpartitioned_mphf.cpp:31-140, include/unpartitioned_mphf.hpp:72-192
 //   essentials::save / load                 pthash/external/essentials/include/essentials.hpp:595-607
+//   pthash::single_phf::build_in_external_memory  (as mphf::build_minimizers_mphf calls it, src/partitioned_mphf.cpp:147-153)
+//   lphash::ef_sequence::encode             include/ef_sequence.hpp:36-75
 //
 // Users: tests/ (to pin the CPU restatement in oracle/lphash_oracle.cpp and to generate the
 // golden fixtures under tests/golden/), bench.py's cpu_baseline / --impl reference legs, and the
@@ -327,6 +329,38 @@ double ref_scan_batch(const char* bases, const uint64_t* offsets, uint64_t n_con
     if (total_kmers) *total_kmers = a;
     if (total_records) *total_records = b;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// minimizer_order for an arbitrary key set: the configuration of src/partitioned_mphf.cpp:45-52 and the call of
+// :147-153, saved with essentials::save to `output`.
+int ref_build_minimizer_phf(const uint64_t* keys, uint64_t n, double c, int threads, const char* tmp_dir,
+                            const char* output) {
+    try {
+        pthash::build_configuration cfg;
+        cfg.minimal_output = true;
+        cfg.seed = lphash::constants::default_pthash_seed;
+        cfg.c = c;
+        cfg.alpha = 0.94;
+        cfg.verbose_output = false;
+        cfg.num_threads = threads;
+        cfg.ram = uint64_t(4) * essentials::GB;
+        cfg.tmp_dir = tmp_dir ? tmp_dir : ".";
+        lphash::pthash_minimizers_mphf_t f;
+        f.build_in_external_memory(keys, n, cfg);
+        essentials::save(f, output);
+        return 0;
+    } catch (std::exception const& e) { return fail(e); }
+}
+
+// ef_sequence::encode(values, n, u) (values already cumulative, as cumulative_iterator hands them over), saved
+// with essentials::save to `output`.
+int ref_ef_sequence(const uint64_t* values, uint64_t n, uint64_t universe, const char* output) {
+    try {
+        lphash::ef_sequence ef;
+        ef.encode(values, n, universe);
+        essentials::save(ef, output);
+        return 0;
+    } catch (std::exception const& e) { return fail(e); }
 }
 
 }  // extern "C"

@@ -65,3 +65,41 @@ def fnv_fold(codes) -> int:
     for v in np.asarray(codes, dtype=np.uint64).tolist():
         h = ((h ^ v) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
     return h
+
+
+# ---- synthetic inputs of build-p Part 3 (branches sequence-derived fixtures never reach) ----
+def splitmix64(n):
+    x = (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+PART3_FIXTURES = {"sparse": (251100, 200, 20), "maximal": (3000, 31, 20), "mixed": (70000, 63, 24)}
+TRIPLET = np.dtype([("itself", "<u8"), ("p1", "u1"), ("size", "u1")])
+
+
+def part3_triplets(name):
+    """the triplet plan of a tests/golden/part3_<name>.npz fixture (tools/make_golden_part3.py): key i = splitmix64(i)"""
+    n, k, m = PART3_FIXTURES[name]
+    t = np.zeros(n, dtype=TRIPLET)
+    t["itself"] = splitmix64(n)
+    if name == "sparse":      # 1100 NONE super-k-mers of the largest size among colliding minimizers
+        t["p1"][:1100] = 100
+        t["size"][:1100] = k - m + 1
+    elif name == "maximal":   # nothing but MAXIMAL: sizes_and_positions stays empty
+        t["p1"] = k - m
+        t["size"] = k - m + 1
+    elif name == "mixed":     # every type, sizes spread
+        r = np.random.default_rng(5)
+        kind = r.integers(0, 5, n)
+        w = k - m + 1
+        size = r.integers(2, w, n)
+        p1 = np.where(kind == 0, size - 1,                      # LEFT (p1 == size-1 < k-m)
+             np.where(kind == 1, k - m,                          # RIGHT (size < w)
+             np.where(kind == 2, k - m, r.integers(0, 1 << 30, n) % np.maximum(size - 1, 1))))  # MAXIMAL / NONE
+        size = np.where(kind == 2, w, size)
+        size = np.where(kind == 4, 0, size)                      # colliding
+        p1 = np.where(kind == 4, 0, p1)
+        t["p1"], t["size"] = p1, size
+    return t

@@ -4,7 +4,9 @@ compiled unmodified by integration/dropin/build_dropin.sh against a shadow of in
 
 query-p prints `query file, mphf file, #k-mers, ns/k-mer streaming, ns/k-mer random` (src/query.cpp:83-86): the
 k-mer count (the streaming pass's; the non-streaming pass must agree or the reference's own assert would fire in
-a debug build) has to equal the reference CLI's and the committed expectation.  build-p --check drives the
+a debug build) has to equal the reference CLI's and the committed expectation.  build-p runs Parts 1-4 on the GPU
+(scan, sort + classify, inverted index, colliding k-mers; the two PTHash constructions stay the reference's own
+CPU calls) and must write the very file and print the very CSV line the reference CLI does; --check then drives the
 GPU-backed class through check_collisions / check_streaming_correctness / check_perfection
 (include/mphf_utils.hpp:51-100), i.e. both branches of operator() contig by contig."""
 import json
@@ -60,11 +62,44 @@ def test_query_p_on_a_file_with_non_acgt_bytes():
     assert n_gpu == n_ref == exp["n_codes"]
 
 
-def test_build_p_check_passes_through_the_gpu_class(tmp_path):
-    need_binaries()
-    out = str(tmp_path / "se.lph")
-    r = subprocess.run([GPU_CLI, "build-p", "-i", os.path.join(CFG1, "se.ust.k31.fa.gz"), "-k", "31", "-m", "16",
-                        "-o", out, "-d", str(tmp_path), "--check"], capture_output=True, text=True, timeout=1800)
+def run_build(cli, src, k, m, out, tmp, extra=(), env=None):
+    t0 = time.perf_counter()
+    r = subprocess.run([cli, "build-p", "-i", src, "-k", str(k), "-m", str(m), "-o", out, "-d", tmp, *extra],
+                       capture_output=True, text=True, timeout=1800, env=env)
     assert r.returncode == 0, r.stderr
-    assert "Everything is ok" in r.stderr, r.stderr[-2000:]
-    assert open(out, "rb").read() == open(LPH, "rb").read()  # build-p itself is the reference's: same file
+    return r.stdout, r.stderr, time.perf_counter() - t0
+
+
+def test_build_p_on_the_gpu_writes_the_reference_file_and_passes_check(tmp_path):
+    need_binaries()
+    src = os.path.join(CFG1, "se.ust.k31.fa.gz")
+    out_gpu, out_ref = str(tmp_path / "gpu.lph"), str(tmp_path / "ref.lph")
+    csv_gpu, err_gpu, wall_gpu = run_build(GPU_CLI, src, 31, 16, out_gpu, str(tmp_path), ["--check"])
+    assert "Everything is ok" in err_gpu, err_gpu[-2000:]
+    csv_ref, _, wall_ref = run_build(REF_CLI, src, 31, 16, out_ref, str(tmp_path))
+    assert csv_gpu == csv_ref  # input file, k, m, collision rate, density bounds, bits per k-mer
+    image = open(out_gpu, "rb").read()
+    assert image == open(out_ref, "rb").read() == open(LPH, "rb").read()
+    print(f"\nbuild-p se.ust.k31 (4.9 M k-mers): reference CLI {wall_ref:.2f} s, GPU drop-in incl. --check {wall_gpu:.2f} s")
+
+
+def test_build_p_64_bit_flavour_and_cpu_switch(tmp_path):
+    """the uint64_t kmer_t binary on a small FASTA; LPHASH_B200_CPU_BUILD=1 forwards the build to the reference"""
+    gpu64, ref64 = GPU_CLI.replace("128", "64"), REF_CLI.replace("128", "64")
+    if not (os.path.exists(gpu64) and os.path.exists(ref64)):
+        pytest.skip("64-bit drop-in binaries not built")
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN_DIR, "k31_m20_u64.npz"))
+    raw, off = z["index_bases"].tobytes(), z["index_offsets"]
+    fa = tmp_path / "index.fa"
+    with open(fa, "wb") as f:
+        for i in range(len(off) - 1):
+            f.write(b">%d\n" % i + raw[int(off[i]):int(off[i + 1])] + b"\n")
+    outs = {}
+    for tag, cli, env in [("gpu", gpu64, None), ("ref", ref64, None),
+                          ("cpu_switch", gpu64, dict(os.environ, LPHASH_B200_CPU_BUILD="1"))]:
+        out = str(tmp_path / (tag + ".lph"))
+        csv, _, _ = run_build(cli, str(fa), 31, 20, out, str(tmp_path), env=env)
+        outs[tag] = (csv, open(out, "rb").read())
+    assert outs["gpu"] == outs["ref"] == outs["cpu_switch"]
+    assert outs["gpu"][1] == open(os.path.join(GOLDEN_DIR, "k31_m20_u64.lph"), "rb").read()

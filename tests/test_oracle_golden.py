@@ -1,7 +1,10 @@
 """The CPU oracle (oracle/lphash_oracle.cpp) against the committed golden vectors that
 tools/make_golden.py generated from the UNMODIFIED reference.  Runs without a GPU and without
 /root/reference."""
+import os
+
 import numpy as np
+import pytest
 
 from oracle import oracle
 
@@ -80,3 +83,43 @@ def test_classify_and_colliding_kmers(golden):
                                 golden.coll_ids, kmer_bits=golden.bits)
     assert km.shape == golden.coll_kmers.shape
     assert np.array_equal(km, golden.coll_kmers)
+
+
+# ---- build-p Part 3 (oracle/invindex.py) ------------------------------------------------------------
+def _sections(image, bits):
+    from lphash_b200 import api  # host-only entry point (parser of the serialized image)
+    return api.lph_sections(image, bits)
+
+
+def test_part3_restatement_reproduces_the_reference_files(golden):
+    """re-key + build_inverted_index restated on the CPU = the wavelet tree and sizes_and_positions bytes of the
+    `.lph` the unmodified reference wrote (src/partitioned_mphf.cpp:92-106, 163-268)"""
+    import struct
+    from oracle import invindex
+    image = open(golden.lph, "rb").read()
+    sec = _sections(image, golden.bits)
+    trip = golden.triplets
+    orders = oracle.phf_positions(image[sec[0]:sec[1]], trip["itself"])
+    counters, body = invindex.build_inverted_index(trip, orders, golden.k, golden.m)
+    assert counters == struct.unpack_from("<QQQQ", image, 26)
+    assert body == image[sec[1]:sec[3]]
+
+
+@pytest.mark.parametrize("name", ["sparse", "maximal", "mixed"])
+def test_part3_restatement_on_synthetic_branches(name):
+    """low width 0 + sparse darray1 blocks with overflow positions, an empty sequence, every type mixed: the
+    Elias-Fano image equals what the reference's own ef_sequence::encode saved (tools/make_golden_part3.py)"""
+    import hashlib
+    from conftest import GOLDEN_DIR, PART3_FIXTURES, part3_triplets
+    from oracle import invindex
+    z = np.load(os.path.join(GOLDEN_DIR, f"part3_{name}.npz"))
+    n, k, m = PART3_FIXTURES[name]
+    trip = part3_triplets(name)
+    orders = oracle.phf_positions(z["minimizer_order"].tobytes(), trip["itself"])
+    assert np.array_equal(np.sort(orders), np.arange(n, dtype=np.uint64))
+    counters, body = invindex.build_inverted_index(trip, orders, k, m)
+    assert list(counters) == [int(v) for v in z["counters"]]
+    assert len(body) == int(z["body_bytes"]) and hashlib.sha256(body).hexdigest() == str(z["body_sha256"])
+    ef = invindex.ef_sequence_image(np.cumsum(invindex.value_lists(trip, orders, k, m)).tolist(),
+                                    int(invindex.value_lists(trip, orders, k, m).sum()))
+    assert hashlib.sha256(ef).hexdigest() == str(z["ef_sha256"])
