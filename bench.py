@@ -88,6 +88,30 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def bind_near_gpu(index: int):
+    """Restricts this rank to the cores of the NUMA node its GPU hangs off, before any pinned buffer exists: the
+    staging buffers of the end-to-end legs are then node-local (first touch), and the 8 ranks of a box stop
+    pulling each other's traffic across the socket link.  Returns a description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"node": None, "note": "single NUMA node"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "note": "no allowed core on the GPU's node; affinity left as is"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cores": len(allowed)}
+    except Exception as e:  # best effort: the bench runs without it
+        return {"node": None, "note": f"not bound ({e})"}
+
+
 def index_path(n_kmers: int) -> str:
     return os.path.join(CACHE, f"cfg2_n{n_kmers}_k{K}_m{M}_u{BITS}.lph")
 
@@ -431,10 +455,16 @@ def run_ours(args):
     bases, offsets, lph = make_workload(args.kmers)
     if world > 1:
         import datetime
+        # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...", printed to stdout
+        # when the environment sets NCCL_DEBUG) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"),
                                 timeout=datetime.timedelta(minutes=30))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    all_cores = os.sched_getaffinity(0)
+    threads = len(all_cores)  # the CPU legs use every core the process may run on (affinity restored below)
+    numa = bind_near_gpu(local) if not os.environ.get("LPHB_BENCH_NO_NUMA") else {"node": None, "note": "disabled"}
     f = api.Mphf.load(lph, BITS, device=local)
     stream = torch.cuda.Stream(device=dev)  # a real stream: the handle attaches its L2 access-policy window to it
     torch.cuda.set_stream(stream)
@@ -448,7 +478,6 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     nocheck = bool(os.environ.get("LPHB_BENCH_NOCHECK"))  # kernel-timing experiments with wrong codes only
-    threads = host_threads()
 
     if workload == "cfg2":
         line = bench_cfg2(args, torch, dist, api, L, f, dev, stream, rank, world, bases, offsets, lph, sync_all,
@@ -464,7 +493,9 @@ def run_ours(args):
         line = bench_cfg5(args, torch, dist, api, L, f, dev, stream, rank, world, bases, lph, sync_all, sampler,
                           nocheck, threads, slabs_total=args.slabs, brief=False)
     if rank == 0:
+        line["config"]["host_numa"] = numa
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cores)
             try:
                 if workload == "cfg2":
                     n, times = cpu_reference_run(bases, offsets, lph, steps=3, warmup=1, threads=threads)

