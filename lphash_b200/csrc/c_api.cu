@@ -1082,7 +1082,7 @@ ClassifySession& classify_session(int device) {
 // Sort by minimizer + classify of n records that are already on the device (stream s); results to host.
 int classify_device(const uint8_t* d_rec, uint64_t n, void* triplets, uint64_t triplets_capacity,
                     uint64_t* n_triplets, uint64_t* ids, uint64_t ids_capacity, uint64_t* n_ids,
-                    cudaStream_t s) {
+                    int key_bits, cudaStream_t s) {
     // workspace kept per device between calls (freed by lphb_scan_release); callers hold the device's mutex
     int dev = 0;
     CK(cudaGetDevice(&dev));
@@ -1101,7 +1101,7 @@ int classify_device(const uint8_t* d_rec, uint64_t n, void* triplets, uint64_t t
     tmp.reserve(tb);
     launch_classify_groups(d_rec, n, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<uint32_t>(),
                            idx2.as<uint32_t>(), flags.as<uint8_t>(), gslot.as<uint32_t>(), cslot.as<uint32_t>(),
-                           counts.as<unsigned long long>(), tmp.p, tb, s);
+                           counts.as<unsigned long long>(), tmp.p, tb, key_bits, s);
     unsigned long long h_counts[2] = {0, 0};
     CK(cudaMemcpyAsync(h_counts, counts.p, sizeof(h_counts), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1233,7 +1233,7 @@ int lphb_classify(int device, const void* records, uint64_t n_records, void* tri
         rec.reserve(n_records * 18 + 64);
         CK(cudaMemcpyAsync(rec.p, records, n_records * 18, cudaMemcpyHostToDevice, fr.s));
         return classify_device(rec.as<uint8_t>(), n_records, triplets, triplets_capacity, n_triplets, ids,
-                               ids_capacity, n_ids, fr.s);
+                               ids_capacity, n_ids, 64, fr.s);  // m unknown here: all key bits
     });
 }
 
@@ -1254,7 +1254,7 @@ int lphb_scan_classify(int device, uint32_t k, uint32_t m, uint64_t seed, const 
         *n_ids = 0;
         if (S.n_records) {  // the records never leave the device
             rc = classify_device(S.records.as<uint8_t>(), S.n_records, triplets, triplets_capacity, n_triplets,
-                                 ids, ids_capacity, n_ids, S.s);
+                                 ids, ids_capacity, n_ids, int(2 * m), S.s);  // a minimizer is 2m bits
             if (rc != LPHB_OK) return rc;
         }
         *mm_count = mm_out;

@@ -90,11 +90,11 @@ uint64_t classify_tmp_bytes(uint64_t n) {
 void launch_classify_groups(const uint8_t* records, uint64_t n, uint64_t* key, uint64_t* key_sorted,
                             uint32_t* idx, uint32_t* idx_sorted, uint8_t* flags, uint32_t* gslot,
                             uint32_t* cslot, unsigned long long* counts, void* d_tmp, uint64_t tmp_bytes,
-                            cudaStream_t stream) {
+                            int key_bits, cudaStream_t stream) {
     if (n) {
         k_rec_keys<<<cgrid(n), 256, 0, stream>>>(records, n, key, idx);
         size_t bytes = tmp_bytes;
-        cub::DeviceRadixSort::SortPairs(d_tmp, bytes, key, key_sorted, idx, idx_sorted, n, 0, 64, stream);
+        cub::DeviceRadixSort::SortPairs(d_tmp, bytes, key, key_sorted, idx, idx_sorted, n, 0, key_bits, stream);
         k_group_flags<<<cgrid(n), 256, 0, stream>>>(key_sorted, n, flags);
         cub::TransformInputIterator<uint32_t, Bit0, const uint8_t*> it0(flags, Bit0{});
         bytes = tmp_bytes;

@@ -49,13 +49,14 @@ void launch_colliding_emit(ScanBatch const& b, uint64_t n_records, const uint32_
                            const uint32_t* take, const uint64_t* out_off, int kmer_bits,
                            uint8_t* kmers, cudaStream_t stream);
 
-// minimizer::classify (classify_kernels.cu).  Step 1: sort by minimizer, group flags (bit 0: first of
+// minimizer::classify (classify_kernels.cu).  Step 1: sort by minimizer (key_bits = significant bits of a
+// minimizer: 2m when the caller knows m, else 64), group flags (bit 0: first of
 // its group, bit 1: member of a group of several), output slots; counts[0] = #triplets, counts[1] = #ids.
 uint64_t classify_tmp_bytes(uint64_t n);
 void launch_classify_groups(const uint8_t* records, uint64_t n, uint64_t* key, uint64_t* key_sorted,
                             uint32_t* idx, uint32_t* idx_sorted, uint8_t* flags, uint32_t* gslot,
                             uint32_t* cslot, unsigned long long* counts, void* d_tmp, uint64_t tmp_bytes,
-                            cudaStream_t stream);
+                            int key_bits, cudaStream_t stream);
 // Step 2: 10-byte triplets in ascending minimizer order, colliding ids gathered and sorted ascending.
 void launch_classify_emit(const uint8_t* records, const uint64_t* key_sorted, const uint32_t* idx_sorted,
                           const uint8_t* flags, const uint32_t* gslot, const uint32_t* cslot, uint64_t n,
