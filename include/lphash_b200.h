@@ -150,10 +150,11 @@ int lphb_mphf_dirty_flags(const lphb_mphf* f, const uint8_t** d_flags, uint64_t*
  * src/partitioned_mphf.cpp:70-77) for a batch of contigs.  records receives packed 18-byte
  * mm_record_t {u64 itself, u64 id, u8 p1, u8 size} (include/constants.hpp:26-33) in scan order;
  * mm_count is the running global m-mer ordinal (in: value before the batch, out: after).
- * Input contract: ACGT/acgt (U/u) only, the k-mer sets lphash is built from (BCALM2/UST unitigs; the
- * reference documents its build as taking "valid k-mers only", src/parser_build.cpp:13-16).  A batch
- * with any other byte is refused with LPHB_E_ARG and produces nothing; the reference would flush the
- * open super-k-mer at the byte and go on (include/minimizer.hpp:138-151), which is not reproduced.
+ * Bytes other than ACGT/acgt (U/u) are handled as the reference's loop does (include/minimizer.hpp:
+ * 138-151): the open super-k-mer is flushed at the byte and the window restarts, m-mer ordinals advance
+ * over valid runs only, and a run of exactly k valid bases that is followed by such a byte counts its
+ * k-mer in *n_kmers without ever emitting a record for it.  (Clean batches - the unitig sets lphash is
+ * built from - take one kernel; a batch with such bytes is cut at them on the device and scanned again.)
  * A batch must hold fewer than 2^32 k-mers and span fewer than 2^32 bases.                         */
 int lphb_scan_superkmers(int device, uint32_t k, uint32_t m, uint64_t seed, const char* bases,
                          const uint64_t* offsets, uint64_t n_contigs, uint64_t* mm_count,

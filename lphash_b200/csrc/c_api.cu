@@ -894,14 +894,15 @@ namespace {
 // Device workspace of the build-side scan, kept per device between calls.
 struct ScanSession {
     DevBuf bases, offsets, code_off, id_base, dirty, head, pos, rank, records, start_pos, tmp, status, tile_ws;
+    DevBuf r_starts, r_flag, r_voff, r_vstart, r_tmp, r_cnt, r_poff, r_pid;  // contigs with non-ACGT bytes: runs, pieces
     cudaStream_t s = nullptr;
     ScanBatch b{};
     uint64_t n_records = 0, n_kmers = 0, tmp_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the record-producing kernels of the last scan
     double kernel_ms = 0;
     ~ScanSession() {
-        for (DevBuf* d : {&bases, &offsets, &code_off, &id_base, &dirty, &head, &pos, &rank, &records,
-                          &start_pos, &tmp, &status, &tile_ws})
+        for (DevBuf* d : {&bases, &offsets, &code_off, &id_base, &dirty, &head, &pos, &rank, &records, &start_pos, &tmp,
+                          &status, &tile_ws, &r_starts, &r_flag, &r_voff, &r_vstart, &r_tmp, &r_cnt, &r_poff, &r_pid})
             d->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -934,28 +935,30 @@ ScanSession& scan_session(int device) {
 // offsets, i.e. d_bases + offsets[0] is the first base): leaves the records (scan order) and the
 // stream position of every record's first k-mer in the session, returns after the device finished.
 // Instantiated (k, m): one fused kernel (query_tiled.cu, kScan form); others: the generic passes.
-int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases,
-                    const uint64_t* d_offsets, const uint64_t* offsets, uint64_t n_contigs, uint64_t mm_count_in,
-                    uint64_t* mm_count_out, ScanTrace& tr) {
+// One pass of the scan kernels over a partition of the stream into contigs.  d_bases is indexed by the offsets;
+// n_kmers = k-mers of the partition; d_id_base = m-mer ordinal of every contig's first m-mer, or null (then
+// mm_count_in + the m-mers of the contigs before it).  *n_dirty = contigs with non-ACGT bytes (their records are
+// meaningless; with `pieces` the partition was cut so that such contigs hold no k-mer at all).
+int scan_pass(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases, const uint64_t* d_offsets,
+              uint64_t n_contigs, uint64_t first, uint64_t span, uint64_t n_kmers, uint64_t n_kmers_cap,
+              const uint64_t* d_id_base, uint64_t mm_count_in, bool pieces, uint64_t* n_dirty, ScanTrace& tr) {
     cudaStream_t s = S.s;
-    const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
-    const uint64_t n_kmers = S.n_kmers;
     S.code_off.reserve((n_contigs + 1) * 8);
     S.id_base.reserve((n_contigs + 1) * 8);
     S.dirty.reserve(n_contigs + 8);
     S.status.reserve(64);
-    S.records.reserve(n_kmers * 18 + 64);       // capacity: one record per k-mer (low-complexity worst case)
-    S.start_pos.reserve((n_kmers + 2) * 4);
+    S.records.reserve(n_kmers_cap * 18 + 64);       // capacity: one record per k-mer (low-complexity worst case)
+    S.start_pos.reserve((n_kmers_cap + 2) * 4);
     const bool tiled = scan_tiled_available(k, m);
-    uint64_t t1 = tiled ? 0 : head_ranks_tmp_bytes(n_kmers > n_contigs ? n_kmers : n_contigs);
+    uint64_t t1 = tiled ? 0 : head_ranks_tmp_bytes(n_kmers_cap > n_contigs ? n_kmers_cap : n_contigs);
     uint64_t t2 = code_offsets_tmp_bytes(n_contigs);
     uint64_t t3 = head_ranks_tmp_bytes(n_contigs);  // the m-mer ordinal scan over contigs
     S.tmp_bytes = std::max(std::max(t1, t2), t3);
     S.tmp.reserve(S.tmp_bytes);
     if (!tiled) {
-        S.head.reserve(n_kmers + 8);
-        S.pos.reserve(n_kmers + 8);
-        S.rank.reserve((n_kmers + 2) * 4);
+        S.head.reserve(n_kmers_cap + 8);
+        S.pos.reserve(n_kmers_cap + 8);
+        S.rank.reserve((n_kmers_cap + 2) * 4);
     }
     S.tile_ws.reserve(query_tiled_ws_bytes(span));
     if (!S.ev0) {
@@ -967,12 +970,19 @@ int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const
     auto* st = S.status.as<unsigned long long>();
     CK(cudaMemsetAsync(st, 0, 64, s));
     launch_code_offsets(d_offsets, n_contigs, k, S.code_off.as<uint64_t>(), st, S.tmp.p, S.tmp_bytes, s);
-    launch_id_base(d_offsets, n_contigs, m, mm_count_in, S.id_base.as<uint64_t>(), S.tmp.p, S.tmp_bytes, s);
+    if (!d_id_base) {
+        launch_id_base(d_offsets, n_contigs, m, mm_count_in, S.id_base.as<uint64_t>(), S.tmp.p, S.tmp_bytes, s);
+        d_id_base = S.id_base.as<uint64_t>();
+    }
+    if (pieces) {  // the partition's k-mer count is only known on the device
+        CK(cudaMemcpyAsync(&n_kmers, S.code_off.as<uint64_t>() + n_contigs, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     ScanBatch& b = S.b;
     b.bases = d_bases;
     b.offsets = d_offsets;
     b.code_off = S.code_off.as<uint64_t>();
-    b.id_base = S.id_base.as<uint64_t>();
+    b.id_base = d_id_base;
     b.n_contigs = n_contigs;
     b.first_base = first;
     b.end_base = first + span;
@@ -981,6 +991,9 @@ int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const
     b.m = m;
     b.seed = seed;
     b.dirty = S.dirty.as<uint8_t>();
+    S.n_records = 0;
+    *n_dirty = 0;
+    if (n_kmers == 0) return LPHB_OK;
     CK(cudaEventRecord(S.ev0, s));
     unsigned long long h_nrec = 0;
     if (tiled) {
@@ -1014,10 +1027,8 @@ int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const
     if (!tiled) CK(cudaMemcpyAsync(&n_rec32, S.rank.as<uint32_t>() + n_kmers, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    if (h_st[1] != 0)
-        return fail(LPHB_E_ARG,
-                    "build input contains non-ACGT bytes (the reference's build requires valid "
-                    "k-mers only, src/parser_build.cpp:13-16); not supported by the GPU scan");
+    *n_dirty = h_st[1];
+    if (h_st[1] != 0 && !pieces) return LPHB_OK;  // the caller cuts the batch at the invalid bytes and comes back
     h_nrec = tiled ? h_st[2] : n_rec32;
     S.n_records = h_nrec;
     if (!tiled) {
@@ -1030,8 +1041,56 @@ int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const
     }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) S.kernel_ms = ms; else cudaGetLastError();
-    (void)mm_count_out;
     return LPHB_OK;
+}
+
+int run_scan_device(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* d_bases,
+                    const uint64_t* d_offsets, const uint64_t* offsets, uint64_t n_contigs, uint64_t mm_count_in,
+                    uint64_t* mm_count_out, ScanTrace& tr) {
+    cudaStream_t s = S.s;
+    const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
+    const uint64_t n_kmers = S.n_kmers;
+    uint64_t n_dirty = 0;
+    int rc = scan_pass(S, k, m, seed, d_bases, d_offsets, n_contigs, first, span, n_kmers, n_kmers, nullptr, mm_count_in,
+                       false, &n_dirty, tr);
+    if (rc != LPHB_OK || n_dirty == 0) return rc;
+    // Contigs with non-ACGT bytes (include/minimizer.hpp:138-151): every maximal valid run is scanned as a contig
+    // of its own (quirk_kernels.cu, build side); k-mer and m-mer totals come from the runs.
+    if (k < 2) return fail(LPHB_E_ARG, "build input with non-ACGT bytes needs k >= 2");
+    const char* rel = d_bases + first;  // positions below are relative to the batch
+    S.r_starts.reserve((n_contigs + 2) * 8);
+    S.r_flag.reserve(span + 8);
+    S.r_voff.reserve((span + 2) * 8);
+    S.r_vstart.reserve((n_contigs + 2) * 4);
+    const uint64_t qt = quirk_tmp_bytes(span + 2);
+    S.r_tmp.reserve(qt);
+    auto* st = S.status.as<unsigned long long>();
+    launch_shift_starts(d_offsets, n_contigs, first, S.r_starts.as<uint64_t>(), s);
+    launch_find_runs(rel, span, S.r_starts.as<uint64_t>(), n_contigs, S.r_flag.as<uint8_t>(), S.r_voff.as<uint64_t>(), st + 4,
+                     S.r_vstart.as<uint32_t>(), S.r_tmp.p, qt, s);
+    unsigned long long n_v = 0;
+    CK(cudaMemcpyAsync(&n_v, st + 4, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    S.r_cnt.reserve(3 * (n_v + 1) * 8);
+    uint64_t *d_pieces = S.r_cnt.as<uint64_t>(), *d_ids = d_pieces + (n_v + 1), *d_kmers = d_ids + (n_v + 1);
+    launch_build_run_counts(rel, S.r_voff.as<uint64_t>(), st + 4, S.r_vstart.as<uint32_t>(), n_contigs, n_v, k, m, d_pieces,
+                            d_ids, d_kmers, S.r_tmp.p, qt, s);
+    uint64_t totals[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(&totals[0], d_pieces + n_v, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&totals[1], d_ids + n_v, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&totals[2], d_kmers + n_v, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n_pieces = totals[0];
+    S.r_poff.reserve((n_pieces + 2) * 8);
+    S.r_pid.reserve((n_pieces + 2) * 8);
+    launch_build_pieces(S.r_voff.as<uint64_t>(), st + 4, n_v, k, d_pieces, d_ids, mm_count_in, span, S.r_poff.as<uint64_t>(),
+                        S.r_pid.as<uint64_t>(), s);
+    tr.mark(s, "runs of valid bases -> pieces");
+    *mm_count_out = mm_count_in + totals[1];
+    rc = scan_pass(S, k, m, seed, rel, S.r_poff.as<uint64_t>(), n_pieces, 0, span, 0, n_kmers, S.r_pid.as<uint64_t>(),
+                   mm_count_in, true, &n_dirty, tr);
+    S.n_kmers = totals[2];  // what from_string returns: the swallowed k-mers of exactly-k runs included
+    return rc;
 }
 
 // Validates a host batch, moves it to the device and scans it.

@@ -64,6 +64,21 @@ void launch_quirk_emit(const uint64_t* d_vcode_off, const uint64_t* d_vcodes, co
                        const uint32_t* d_spur_cnt, uint32_t w_cap, uint64_t n_v_host, const unsigned long long* d_n_v,
                        const uint64_t* d_out_off, uint64_t total_hint, uint64_t* d_out, cudaStream_t stream);
 
+// Build side (minimizer::from_string over contigs with non-ACGT bytes): launch_find_runs over the whole batch
+// (d_starts = contig starts relative to the batch, launch_shift_starts), then per run r the number of pieces the
+// scan kernels get it in (1 for a run they must scan; invalid runs and runs of exactly k bases followed by an
+// invalid byte are cut into pieces of k-1 bytes, which hold no k-mer), its m-mer ordinals and k-mers - exclusive
+// sums in place, entry n_v = totals - and finally the piece offsets (n_pieces + 1, relative to the batch) with the
+// m-mer ordinal of every piece's first m-mer.
+void launch_shift_starts(const uint64_t* d_offsets, uint64_t n_contigs, uint64_t first, uint64_t* d_starts, cudaStream_t stream);
+void launch_build_run_counts(const char* d_bases, const uint64_t* d_voff, const unsigned long long* d_n_v,
+                             const uint32_t* d_vstart, uint64_t n_list, uint64_t n_v_host, uint32_t k, uint32_t m,
+                             uint64_t* d_pieces, uint64_t* d_ids, uint64_t* d_kmers, void* d_tmp, uint64_t tmp_bytes,
+                             cudaStream_t stream);
+void launch_build_pieces(const uint64_t* d_voff, const unsigned long long* d_n_v, uint64_t n_v_host, uint32_t k,
+                         const uint64_t* d_pieces, const uint64_t* d_ids, uint64_t mm_count_in, uint64_t n, uint64_t* d_poff,
+                         uint64_t* d_pid, cudaStream_t stream);
+
 // dst[dst_off[c] .. dst_off[c+1]) = src_c[src_off[c] ..) where src_c = from_b[c] ? src_b : src_a (`total` = dst_off[n_contigs])
 void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src_a,
                      const uint64_t* src_b, const uint64_t* src_off, const uint8_t* from_b,

@@ -289,6 +289,61 @@ __global__ void k_contig_counts(const uint64_t* out_off, const uint32_t* vstart,
     counts[j] = out_off[vstart[j + 1]] - out_off[vstart[j]];
 }
 
+
+// ---- build side: minimizer::from_string over contigs with non-ACGT bytes (include/minimizer.hpp:138-151) ----
+// An invalid byte flushes the open super-k-mer and restarts the window, so every maximal valid run is scanned like
+// a contig of its own, with two exceptions the reference's loop has: m-mer ordinals (`id`) advance over valid runs
+// only, and a run of exactly k bases that is FOLLOWED by an invalid byte counts its k-mer but never emits it (the
+// first window is only searched when base k+1 arrives or the contig ends, minimizer.hpp:59-74, 153-162).  The scan
+// kernels take a partition of the stream into contigs; the partition handed to them cuts invalid runs and those
+// swallowed runs into pieces shorter than k, which hold no k-mer.
+__global__ void k_shift_starts(const uint64_t* offsets, uint64_t n_contigs, uint64_t first, uint64_t* starts) {
+    const uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (c <= n_contigs) starts[c] = offsets[c] - first;
+}
+__global__ void k_build_run_counts(const char* bases, const uint64_t* voff, const unsigned long long* n_v_p,
+                                   const uint32_t* vstart, uint64_t n_list, uint32_t k, uint32_t m, uint64_t* pieces,
+                                   uint64_t* ids, uint64_t* kmers) {
+    const uint64_t n_v = *n_v_p;
+    const uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (r > n_v) return;
+    if (r == n_v) {
+        pieces[r] = ids[r] = kmers[r] = 0;
+        return;
+    }
+    const uint64_t L = voff[r + 1] - voff[r];
+    const bool valid = nt4(uint8_t(bases[voff[r]])) < 4;
+    bool swallowed = false;
+    if (valid && L == k) {  // followed by an invalid byte of the same contig?
+        uint64_t lo = 0, hi = n_list;  // first j with vstart[j] >= r + 1 (vstart[n_list] = n_v)
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (vstart[mid] < r + 1) lo = mid + 1; else hi = mid;
+        }
+        swallowed = vstart[lo] != r + 1;
+    }
+    const uint64_t step = k - 1;
+    pieces[r] = (valid && !swallowed) ? 1 : (L + step - 1) / step;
+    ids[r] = valid && L >= m ? L - m + 1 : 0;
+    kmers[r] = valid && L >= k ? L - k + 1 : 0;
+}
+__global__ void k_build_pieces(const uint64_t* voff, const unsigned long long* n_v_p, uint32_t k, const uint64_t* pieces,
+                               const uint64_t* ids, uint64_t mm_count_in, uint64_t n, uint64_t* poff, uint64_t* pid) {
+    const uint64_t n_v = *n_v_p;
+    const uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (r > n_v) return;
+    if (r == n_v) {
+        poff[pieces[r]] = n;
+        pid[pieces[r]] = mm_count_in + ids[r];
+        return;
+    }
+    const uint64_t first = pieces[r], cnt = pieces[r + 1] - first, step = k - 1;
+    for (uint64_t i = 0; i < cnt; ++i) {
+        poff[first + i] = voff[r] + i * step;
+        pid[first + i] = mm_count_in + ids[r] + i * step;  // only read for single-piece (scanned) runs
+    }
+}
+
 unsigned blocks_for(uint64_t n, unsigned cap = 148 * 32) {
     uint64_t b = (n + 255) / 256;
     if (b < 1) b = 1;
@@ -363,6 +418,30 @@ void launch_assemble(uint64_t* dst, const uint64_t* dst_off, const uint64_t* src
                      const uint64_t* src_off, const uint8_t* from_b, uint64_t n_contigs, uint64_t total, cudaStream_t stream) {
     if (!n_contigs || !total) return;
     segcopy<uint64_t>(dst, dst_off, n_contigs, nullptr, total, ContigCodes{src_a, src_b, src_off, from_b}, stream);
+}
+
+void launch_shift_starts(const uint64_t* d_offsets, uint64_t n_contigs, uint64_t first, uint64_t* d_starts, cudaStream_t stream) {
+    k_shift_starts<<<unsigned((n_contigs + 256) / 256), 256, 0, stream>>>(d_offsets, n_contigs, first, d_starts);
+}
+
+// per run: pieces / m-mer ordinals / k-mers, then exclusive sums in place (entry n_v = totals)
+void launch_build_run_counts(const char* d_bases, const uint64_t* d_voff, const unsigned long long* d_n_v,
+                             const uint32_t* d_vstart, uint64_t n_list, uint64_t n_v_host, uint32_t k, uint32_t m,
+                             uint64_t* d_pieces, uint64_t* d_ids, uint64_t* d_kmers, void* d_tmp, uint64_t tmp_bytes,
+                             cudaStream_t stream) {
+    k_build_run_counts<<<unsigned((n_v_host + 256) / 256), 256, 0, stream>>>(d_bases, d_voff, d_n_v, d_vstart, n_list, k, m,
+                                                                             d_pieces, d_ids, d_kmers);
+    for (uint64_t* a : {d_pieces, d_ids, d_kmers}) {
+        size_t bytes = tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(d_tmp, bytes, a, a, n_v_host + 1, stream);
+    }
+}
+
+void launch_build_pieces(const uint64_t* d_voff, const unsigned long long* d_n_v, uint64_t n_v_host, uint32_t k,
+                         const uint64_t* d_pieces, const uint64_t* d_ids, uint64_t mm_count_in, uint64_t n, uint64_t* d_poff,
+                         uint64_t* d_pid, cudaStream_t stream) {
+    k_build_pieces<<<unsigned((n_v_host + 256) / 256), 256, 0, stream>>>(d_voff, d_n_v, k, d_pieces, d_ids, mm_count_in, n,
+                                                                         d_poff, d_pid);
 }
 
 }  // namespace lphb

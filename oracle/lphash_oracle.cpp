@@ -605,31 +605,82 @@ static void classify(std::vector<Record> recs, std::vector<Triplet>& uniq, std::
     std::sort(ids.begin(), ids.end());
 }
 
-// a15  get_colliding_kmers restated through S2': all forward k-mers of every super-k-mer whose
-// minimizer-occurrence id is in the ascending id list, in scan order (clean contigs).
-// ref: include/minimizer.hpp:172-319; caller src/partitioned_mphf.cpp:120-129.
+// a15  get_colliding_kmers, sequential restatement incl. its behaviour around invalid bytes: the same window
+// walk as from_string with the k-mers of the open super-k-mer buffered; a super-k-mer is written out when it closes
+// and the id of its minimizer occurrence is the next one of the ascending id list (one forward cursor, as the
+// reference's `itr`).  ref: include/minimizer.hpp:172-319; caller src/partitioned_mphf.cpp:120-129.
+static void colliding_kmers_contig(const char* s, u64 len, unsigned k, unsigned m, u64 seed, const u64* ids, u64 n_ids,
+                                   u64& next_id, u64& mm_count, std::vector<u128>& out) {
+    const u64 w = k - m + 1;
+    const u64 mm_mask = (u64(1) << (2 * m)) - 1;
+    const u128 km_mask = (u128(1) << (2 * k)) - 1;
+    struct Slot {
+        u64 hash = 0, id = 0;
+    };
+    std::vector<Slot> ring(w);
+    std::vector<u128> open;  // k-mers of the open super-k-mer
+    u64 cursor = 0, min_slot = w, run = 0, mmer = 0;
+    u128 kmer = 0;
+    auto close = [&]() {  // :241-246, :287-291, :311-316
+        if (next_id < n_ids && ids[next_id] == ring[min_slot].id) {
+            out.insert(out.end(), open.begin(), open.end());
+            ++next_id;
+        }
+    };
+    auto first_window = [&]() {  // :226-232 / :303-309
+        min_slot = 0;
+        for (u64 j = 0; j < w; ++j)
+            if (ring[j].hash < ring[min_slot].hash) min_slot = j;
+    };
+    for (u64 i = 0; i < len; ++i) {
+        int c = nt4((unsigned char)s[i]);
+        if (c > 3) {  // :283-300
+            run = 0;
+            if (min_slot < w) close();
+            open.clear();
+            min_slot = w;
+            cursor = 0;
+            continue;
+        }
+        mmer = ((mmer << 2) | u64(c)) & mm_mask;
+        kmer = ((kmer << 2) | u128(c)) & km_mask;
+        ++run;
+        if (run < m) continue;
+        Slot cur;
+        cur.hash = murmur64(mmer, seed);
+        cur.id = mm_count++;
+        bool rescan = false;
+        if (run == k + 1) first_window();
+        if (run >= k + 1) {
+            if (cursor % w == min_slot || cur.hash < ring[min_slot].hash) {  // :238-256
+                close();
+                open.clear();
+                if (cursor % w == min_slot) rescan = true;
+                else min_slot = cursor;
+            }
+        }
+        ring[cursor] = cur;
+        cursor = (cursor + 1) % w;
+        if (run >= k) open.push_back(kmer);
+        if (rescan) {  // :265-276
+            min_slot = cursor;
+            for (u64 j = (cursor + 1) % w; j < w; ++j)
+                if (ring[min_slot].hash > ring[j].hash) min_slot = j;
+            for (u64 j = 0; j <= cursor; ++j)
+                if (ring[min_slot].hash > ring[j].hash) min_slot = j;
+        }
+    }
+    if (run == k) first_window();
+    if (min_slot < w) close();
+}
+
 static void colliding_kmers(const char* bases, const u64* offsets, u64 n_contigs, unsigned k,
                             unsigned m, u64 seed, const u64* ids, u64 n_ids,
                             std::vector<u128>& out) {
-    u64 mm_count = 0;
-    const u128 km_mask = (u128(1) << (2 * k)) - 1;
-    for (u64 c = 0; c < n_contigs; ++c) {
-        const char* s = bases + offsets[c];
-        u64 len = offsets[c + 1] - offsets[c];
-        std::vector<Record> recs;
-        scan_stateless(s, len, k, m, seed, mm_count, recs);
-        u64 pos = 0;  // k-mer index of the current record's first k-mer
-        for (Record const& r : recs) {
-            if (std::binary_search(ids, ids + n_ids, r.id)) {
-                for (u64 i = pos; i < pos + r.size; ++i) {
-                    u128 km = 0;
-                    for (u64 j = 0; j < k; ++j) km = (km << 2) | u128(nt4((unsigned char)s[i + j]));
-                    out.push_back(km & km_mask);
-                }
-            }
-            pos += r.size;
-        }
-    }
+    u64 mm_count = 0, next_id = 0;
+    for (u64 c = 0; c < n_contigs; ++c)
+        colliding_kmers_contig(bases + offsets[c], offsets[c + 1] - offsets[c], k, m, seed, ids, n_ids, next_id, mm_count,
+                               out);
 }
 
 }  // namespace orc

@@ -138,3 +138,60 @@ def test_synthetic_branches_match_the_restatement(name):
         _, want = invindex.build_inverted_index(trip, oracle.phf_positions(phf, trip["itself"]), k, m)
         first = next(i for i in range(len(want)) if want[i] != body[i])
         pytest.fail(f"body differs from the restatement at byte {first} (wtree {info.wtree_bytes} bytes)")
+
+
+# ---- build input with non-ACGT bytes (include/minimizer.hpp:138-151) --------------------------------
+def dirty_build_batch(k, m, seed):
+    """contigs whose valid runs hit every case of the reference's loop: runs shorter than m / than k, of exactly
+    k bases followed by an invalid byte (k-mer counted, never emitted), of exactly k bases at a contig end
+    (emitted), long runs, long runs of N, contigs that start / end with N, empty and all-N contigs; a few runs are
+    repeated so that some minimizers collide (ids for get_colliding_kmers)"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+
+    def run(n):
+        return rng.choice(acgt[:4] if rng.random() < 0.8 else acgt, int(n))
+
+    N, junk = np.array([78], np.uint8), np.array([45], np.uint8)
+    rep = run(3 * k)
+    contigs = [
+        np.concatenate([run(100), N, run(k), N, run(50), N, N, run(k - 1), junk, run(k)]),
+        run(200),
+        np.concatenate([N, run(k), junk, run(k + 1), np.repeat(N, 5 * k + 3), run(500), N]),
+        np.repeat(N, 10), np.zeros(0, np.uint8), run(k), run(k - 1),
+        np.concatenate([run(m - 1), N, run(m), N, rep, N, run(2 * k), N, rep, np.repeat(N, k - 1), rep[: 2 * k]]),
+        np.concatenate([run(4000), N, run(3000), junk, run(k), N]),
+        run(2500),
+    ]
+    bases = np.concatenate(contigs).astype(np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    return bases, offsets
+
+
+@pytest.mark.parametrize("k,m", [(31, 20), (63, 24), (15, 7), (25, 13)])  # fused scan kernel (W <= 17, wide) / generic passes
+def test_build_input_with_non_acgt_bytes_matches_the_reference_loop(k, m):
+    from oracle import oracle
+    bases, offsets = dirty_build_batch(k, m, seed=k)
+    want, wk, wmm = oracle.scan(bases, offsets, k, m, mode=0, mm_count=5)
+    got, gk, gmm = api.scan_superkmers(bases, offsets, k, m, mm_count=5)
+    assert (gk, gmm) == (wk, wmm)
+    assert np.array_equal(got, want)
+    # Parts 1 + 2 fused, and Part 4 on the same input
+    want0, _, wmm0 = oracle.scan(bases, offsets, k, m, mode=0)
+    trip_w, ids_w = oracle.classify(want0)
+    trip, ids, nk, mm = api.scan_classify(bases, offsets, k, m)
+    assert nk == wk and mm == wmm0 and np.array_equal(trip, trip_w) and np.array_equal(ids, ids_w)
+    assert len(ids) > 0
+    bits = 128 if k > 31 else 64
+    km_w = oracle.colliding_kmers(bases, offsets, k, m, ids_w, kmer_bits=bits)
+    km = api.colliding_kmers(bases, offsets, k, m, ids, kmer_bits=bits)
+    assert np.array_equal(km, km_w)
+    # a batch that does not start at offset 0, clean contigs after a dirty call
+    sub = offsets[2:7]
+    want2, wk2, _ = oracle.scan(bases[int(sub[0]):int(sub[-1])], sub - sub[0], k, m, mode=0)
+    got2, gk2, _ = api.scan_superkmers(bases, sub, k, m)
+    assert gk2 == wk2 and np.array_equal(got2, want2)
+    clean, coff = bases[int(offsets[1]):int(offsets[2])], np.array([0, offsets[2] - offsets[1]], np.uint64)
+    want3, _, _ = oracle.scan(clean, coff, k, m, mode=0)
+    got3, _, _ = api.scan_superkmers(clean, coff, k, m)
+    assert np.array_equal(got3, want3)

@@ -47,3 +47,21 @@ def test_bundled_index_scan_matches_reference():
     rec, nk, mm = api.scan_superkmers(bases, offsets, 31, 16)
     assert (len(rec), nk, mm) == (exp["records"], exp["n_kmers"], exp["mm_count"])
     assert hashlib.sha256(rec.tobytes()).hexdigest() == exp["sha256_records"]
+
+
+@pytest.mark.parametrize("name", ["ecoli1", "srr"])
+def test_build_side_on_bundled_files_with_non_acgt_bytes(name):
+    """Parts 1, 2 and 4 of build-p over ecoli1.fasta (50 runs of N) and the FASTQ (105 reads with N) against what
+    the reference's from_string / classify / get_colliding_kmers returned for them (include/minimizer.hpp:138-151)"""
+    exp = json.load(open(os.path.join(CFG1, "expected.json")))
+    e = exp["scan_dirty"][name]
+    bases, offsets = seqio.read_batch(os.path.join(CFG1, exp["queries"][name]["file"]))
+    rec, nk, mm = api.scan_superkmers(bases, offsets, 31, 16)
+    assert (len(rec), nk, mm) == (e["records"], e["n_kmers"], e["mm_count"])
+    assert hashlib.sha256(rec.tobytes()).hexdigest() == e["sha256_records"]
+    trip, ids, nk2, mm2 = api.scan_classify(bases, offsets, 31, 16)
+    assert (nk2, mm2) == (nk, mm)
+    assert hashlib.sha256(trip.tobytes()).hexdigest() == e["sha256_triplets"] and sha(ids) == e["sha256_ids"]
+    km = api.colliding_kmers(bases, offsets, 31, 16, ids, kmer_bits=128)
+    assert len(km) == e["colliding_kmers"]
+    assert hashlib.sha256(np.ascontiguousarray(km).tobytes()).hexdigest() == e["sha256_colliding_kmers"]

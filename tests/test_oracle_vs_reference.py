@@ -62,3 +62,20 @@ def test_oracle_scan_matches_reference():
     rec, nk, mm = oracle.scan(bases, offsets, 31, 16, mode=0)
     assert (len(rec), nk, mm) == (exp["records"], exp["n_kmers"], exp["mm_count"])
     assert hashlib.sha256(rec.tobytes()).hexdigest() == exp["sha256_records"]
+
+
+@pytest.mark.parametrize("name", ["ecoli1", "srr"])
+def test_oracle_build_side_on_input_with_non_acgt_bytes(name):
+    """from_string / classify / get_colliding_kmers over files WITH invalid bytes (the reference flushes the open
+    super-k-mer at each one and restarts the window, include/minimizer.hpp:138-151, 283-300)"""
+    exp = expected()["scan_dirty"][name]
+    bases, offsets = seqio.read_batch(os.path.join(CFG1, expected()["queries"][name]["file"]))
+    rec, nk, mm = oracle.scan(bases, offsets, 31, 16, mode=0)
+    assert (len(rec), nk, mm) == (exp["records"], exp["n_kmers"], exp["mm_count"])
+    assert hashlib.sha256(rec.tobytes()).hexdigest() == exp["sha256_records"]
+    trip, ids = oracle.classify(rec)
+    assert hashlib.sha256(trip.tobytes()).hexdigest() == exp["sha256_triplets"]
+    assert sha(ids) == exp["sha256_ids"]
+    km = oracle.colliding_kmers(bases, offsets, 31, 16, ids, kmer_bits=128)
+    assert len(km) == exp["colliding_kmers"]
+    assert hashlib.sha256(np.ascontiguousarray(km).tobytes()).hexdigest() == exp["sha256_colliding_kmers"]

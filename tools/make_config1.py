@@ -72,6 +72,23 @@ def main():
     exp["scan"] = {"records": int(len(rec)), "n_kmers": int(nk), "mm_count": int(mm),
                    "sha256_records": hashlib.sha256(rec.tobytes()).hexdigest()}
     print("scan", exp["scan"])
+    # the reference's build-side loops on input WITH non-ACGT bytes (include/minimizer.hpp:138-151, 283-300):
+    # ecoli1.fasta (50 runs of N) and the FASTQ (105 reads with N) through from_string, classify and
+    # get_colliding_kmers
+    exp["scan_dirty"] = {}
+    for name in ("ecoli1", "srr"):
+        bases, offsets = seqio.read_batch(os.path.join(REF_DATA, FILES[name]))
+        rec, nk, mm = ref.scan(bases, offsets, K, M, bits=BITS)
+        trip, ids = ref.classify(bases, offsets, K, M, bits=BITS)
+        km = ref.colliding_kmers(bases, offsets, K, M, ids, bits=BITS)
+        exp["scan_dirty"][name] = {"records": int(len(rec)), "n_kmers": int(nk), "mm_count": int(mm),
+                                   "sha256_records": hashlib.sha256(rec.tobytes()).hexdigest(),
+                                   "triplets": int(len(trip)), "colliding_ids": int(len(ids)),
+                                   "sha256_triplets": hashlib.sha256(trip.tobytes()).hexdigest(),
+                                   "sha256_ids": hashlib.sha256(np.ascontiguousarray(ids, dtype="<u8").tobytes()).hexdigest(),
+                                   "colliding_kmers": int(len(km)),
+                                   "sha256_colliding_kmers": hashlib.sha256(np.ascontiguousarray(km).tobytes()).hexdigest()}
+        print("scan_dirty", name, exp["scan_dirty"][name])
     json.dump(exp, open(os.path.join(OUT, "expected.json"), "w"), indent=1)
 
 
