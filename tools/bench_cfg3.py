@@ -8,7 +8,9 @@ bench_cache/ does not hold it - the 459 MB file does not fit a gpurun snapshot).
 workload: a random 2.5e9-base genome holds a repeated 31-mer with probability ~0.5, which the reference's build
 rejects (tools/build_cfg3_index.py); 0x5EED0013 builds.
 
-One JSON line per row: cfg3_index (build + load: image bytes, host decode / H2D split), cfg3_query, cfg3_scan."""
+One JSON line per row: cfg3_index (build + load: image bytes, host decode / H2D split), cfg3_query, cfg3_scan, and
+cfg3_build: build-p Parts 1-3 on the GPU at this size (slab-wise scan, sort + classify of all 3.8e8 records, inverted
+index around the reference's minimizer_order) with the assembled `.lph` compared byte for byte with the reference's."""
 import json
 import os
 import sys
@@ -136,6 +138,51 @@ def main():
                       "parity": ["record count == distinct minimizers + repeats; per-slab k-mer counts equal; the scan records "
                                  "themselves are compared in full at config-2 size (tools/bench_rows.py scan)"]}), flush=True)
     f.close()
+    build_row(bases, offsets, lph, plan, peak)
+
+
+def build_row(bases, offsets, lph, plan, peak):
+    import struct
+    image = open(lph, "rb").read()
+    sec = api.lph_sections(image, BITS)
+    seed, nkmers, distinct = struct.unpack_from("<QQQ", image, 2)
+    t0 = time.perf_counter()
+    recs, mm, nk_total = [], 0, 0
+    for (c0, c1) in plan:  # Part 1, slab by slab (a batch holds < 2^32 k-mers; the records of a slab fit a host buffer)
+        sb, so = shard.take(bases, offsets, (c0, c1))
+        r, nk, mm = api.scan_superkmers(sb, so, K, M, seed, mm_count=mm)
+        recs.append(r.copy())
+        nk_total += nk
+        del r, sb
+    api.lib().lphb_scan_release(0)
+    rec = np.concatenate(recs)
+    del recs
+    t1 = time.perf_counter()
+    trip, ids = api.classify(rec)  # Part 2
+    n_rec = len(rec)
+    del rec
+    t2 = time.perf_counter()
+    assert nk_total == nkmers and len(trip) == distinct, (nk_total, nkmers, len(trip), distinct)
+    mo = image[sec[0]:sec[1]]
+    info, body = api.build_inverted_index(K, M, mo, trip)  # Part 3
+    t3 = time.perf_counter()
+    same_body = body == image[sec[1]:sec[3]]
+    out = api.lph_assemble(K, M, seed, nkmers, distinct, info, mo, body, image[sec[3]:sec[4]])
+    t4 = time.perf_counter()
+    same_file = out == image
+    algo = 10 * distinct + len(body)
+    print(json.dumps({"row": "cfg3_build", "metric": "build-p Parts 1-3 on the GPU", "kmers": int(nkmers), "records": int(n_rec),
+                      "distinct_minimizers": int(distinct), "colliding_ids": int(len(ids)),
+                      "colliding_minimizers": int(info.colliding_minimizers),
+                      "part1_scan_s": t1 - t0, "part2_sort_classify_s": t2 - t1, "part3_inverted_index_s": t3 - t2,
+                      "part3_device_ms": info.device_ms, "assemble_s": t4 - t3, "body_bytes": len(body),
+                      "roofline_part3": {"bound": "hbm", "achieved": algo / (info.device_ms * 1e-3) / 1e9, "peak": peak,
+                                         "unit": "GB/s", "frac": algo / (info.device_ms * 1e-3) / 1e9 / peak,
+                                         "algorithmic_bytes": int(algo)},
+                      "parity": {"inverted_index_equals_reference_file": bool(same_body),
+                                 "assembled_lph_equals_reference_file": bool(same_file)},
+                      "note": "host buffers throughout (pageable); PTHash functions taken from the reference's file"}), flush=True)
+    assert same_body and same_file
 
 
 if __name__ == "__main__":
