@@ -223,6 +223,24 @@ int lphb_build_inverted_index(int device, uint32_t k, uint32_t m, const void* mi
                               void* out, uint64_t out_capacity, uint64_t* out_bytes,
                               lphb_inverted_index* info);
 
+/* The same for the unpartitioned variant (build-u, lphash::mphf_alt; src/unpartitioned_mphf.cpp:78-96 re-key and
+ * :152-169 build_pos_index / build_size_index): out receives the image of `positions` (Elias-Fano of the prefix sums
+ * of p1 in minimizer_order order) followed by the image of `sizes` (include/unpartitioned_mphf.hpp:206-207);
+ * lphb_inverted_index_bound(n_triplets) suffices as capacity.                                              */
+typedef struct lphb_inverted_index_alt {
+    uint64_t num_kmers_in_main_index;      /* last prefix sum of the sizes (src/unpartitioned_mphf.cpp:168) */
+    uint64_t positions_bytes, sizes_bytes; /* the two images inside out */
+    double device_ms;
+} lphb_inverted_index_alt;
+int lphb_build_inverted_index_alt(int device, const void* minimizer_order, uint64_t minimizer_order_bytes,
+                                  const void* triplets, uint64_t n_triplets, void* out, uint64_t out_capacity,
+                                  uint64_t* out_bytes, lphb_inverted_index_alt* info);
+int lphb_lph_assemble_alt(uint32_t k, uint32_t m, uint64_t mm_seed, uint64_t nkmers, uint64_t distinct_minimizers,
+                          const lphb_inverted_index_alt* index, const void* minimizer_order,
+                          uint64_t minimizer_order_bytes, const void* index_body, uint64_t index_body_bytes,
+                          const void* fallback_kmer_order, uint64_t fallback_bytes, void* out,
+                          uint64_t out_capacity, uint64_t* out_bytes);
+
 /* ---- the `.lph` writer (host only) ------------------------------------------------------------
  * lphb_lph_assemble lays out a complete serialized lphash::mphf in the visitor order of
  * include/partitioned_mphf.hpp:204-219 - what essentials::save(hf, file) writes (src/build.cpp:52) -

@@ -48,6 +48,11 @@ class InvertedIndex(C.Structure):
                 ("wtree_bytes", C.c_uint64), ("ef_bytes", C.c_uint64), ("device_ms", C.c_double)]
 
 
+class InvertedIndexAlt(C.Structure):
+    _fields_ = [("num_kmers_in_main_index", C.c_uint64), ("positions_bytes", C.c_uint64), ("sizes_bytes", C.c_uint64),
+                ("device_ms", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("dirty_contigs", C.c_uint64), ("kernel_ms", C.c_double)]
@@ -61,7 +66,8 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_query_stream_runs", "lphb_expand_runs", "lphb_mphf_dirty_flags",
            "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming",
            "lphb_mphf_alt_load_file", "lphb_mphf_alt_load_memory", "lphb_inverted_index_bound",
-           "lphb_build_inverted_index", "lphb_lph_assemble", "lphb_lph_sections"]
+           "lphb_build_inverted_index", "lphb_lph_assemble", "lphb_lph_sections", "lphb_build_inverted_index_alt",
+           "lphb_lph_assemble_alt"]
 
 _lib = None
 
@@ -111,6 +117,9 @@ def lib() -> C.CDLL:
     L.lphb_lph_assemble.argtypes = [C.c_uint32, C.c_uint32, u64, u64, u64, C.POINTER(InvertedIndex), p, u64, p, u64, p,
                                     u64, p, u64, C.POINTER(u64)]
     L.lphb_lph_sections.argtypes = [p, u64, i32, i32, C.POINTER(u64)]
+    L.lphb_build_inverted_index_alt.argtypes = [i32, p, u64, p, u64, p, u64, C.POINTER(u64), C.POINTER(InvertedIndexAlt)]
+    L.lphb_lph_assemble_alt.argtypes = [C.c_uint32, C.c_uint32, u64, u64, u64, C.POINTER(InvertedIndexAlt), p, u64, p, u64,
+                                        p, u64, p, u64, C.POINTER(u64)]
     L.lphb_host_free.argtypes = [p]
     for name in EXPORTS:
         if getattr(L, name).restype is C.c_int:
@@ -383,4 +392,33 @@ def lph_assemble(k: int, m: int, mm_seed: int, nkmers: int, distinct_minimizers:
     nb = C.c_uint64(0)
     _check(lib().lphb_lph_assemble(k, m, mm_seed, nkmers, distinct_minimizers, C.byref(index), mo.ctypes.data, len(mo),
                                    body.ctypes.data, len(body), fb.ctypes.data, len(fb), out.ctypes.data, cap, C.byref(nb)))
+    return out[: nb.value].tobytes()
+
+
+def build_inverted_index_alt(minimizer_order: bytes, triplets, device: int = 0):
+    """build-u Part 3 (mphf_alt: /root/reference/src/unpartitioned_mphf.cpp:78-96, 152-169).
+    Returns (InvertedIndexAlt, body bytes = image of positions + image of sizes)."""
+    trip = np.ascontiguousarray(triplets, dtype=TRIPLET_DTYPE)
+    phf = np.frombuffer(minimizer_order, dtype=np.uint8)
+    cap = lib().lphb_inverted_index_bound(len(trip))
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    info = InvertedIndexAlt()
+    nb = C.c_uint64(0)
+    _check(lib().lphb_build_inverted_index_alt(device, phf.ctypes.data, len(phf), trip.ctypes.data, len(trip),
+                                               out.ctypes.data, cap, C.byref(nb), C.byref(info)))
+    return info, out[: nb.value].tobytes()
+
+
+def lph_assemble_alt(k: int, m: int, mm_seed: int, nkmers: int, distinct_minimizers: int, index: InvertedIndexAlt,
+                     minimizer_order: bytes, index_body: bytes, fallback_kmer_order: bytes) -> bytes:
+    """A complete serialized lphash::mphf_alt (what build-u saves) from its parts.  Host only."""
+    mo = np.frombuffer(minimizer_order, dtype=np.uint8)
+    body = np.frombuffer(index_body, dtype=np.uint8)
+    fb = np.frombuffer(fallback_kmer_order, dtype=np.uint8)
+    cap = 34 + len(mo) + len(body) + len(fb)
+    out = np.empty(cap, dtype=np.uint8)
+    nb = C.c_uint64(0)
+    _check(lib().lphb_lph_assemble_alt(k, m, mm_seed, nkmers, distinct_minimizers, C.byref(index), mo.ctypes.data, len(mo),
+                                       body.ctypes.data, len(body), fb.ctypes.data, len(fb), out.ctypes.data, cap,
+                                       C.byref(nb)))
     return out[: nb.value].tobytes()

@@ -50,6 +50,29 @@ __global__ void k_rekey(const __grid_constant__ DevPhf phf, const uint8_t* tripl
     }
 }
 
+// build-u (mphf_alt, ref src/unpartitioned_mphf.cpp:78-96): the triplet itself at its order, no types
+__global__ void k_rekey_alt(const __grid_constant__ DevPhf phf, const uint8_t* triplets, uint64_t n, uint32_t* cells,
+                            unsigned long long* bad) {
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint16_t* t = reinterpret_cast<const uint16_t*>(triplets + 10 * i);
+        const uint64_t itself = uint64_t(t[0]) | (uint64_t(t[1]) << 16) | (uint64_t(t[2]) << 32) | (uint64_t(t[3]) << 48);
+        const uint64_t order = phf_position(phf, murmur64(itself, phf.seed));
+        if (order >= n) {
+            atomicAdd(bad, 1ull);
+            continue;
+        }
+        cells[order] = 0x80000000u | t[4];  // p1 | size << 8
+    }
+}
+__global__ void k_split_alt(const uint32_t* cells, uint64_t n, uint8_t* p1, uint8_t* size, unsigned long long* unset) {
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t c = cells[i];
+        if (!(c >> 31)) atomicAdd(unset, 1ull);
+        p1[i] = uint8_t(c);
+        size[i] = uint8_t(c >> 8);
+    }
+}
+
 // one-hot of a cell's class in four 16-bit lanes: left, rc, none, msb
 __device__ __forceinline__ uint64_t class_lanes(uint32_t cell) {
     if (!(cell >> 31)) return 0;
@@ -220,6 +243,15 @@ void launch_rekey(DevPhf const& phf, const uint8_t* triplets, uint64_t n, uint32
                   unsigned long long* bad, unsigned long long* colliding, cudaStream_t s) {
     if (!n) return;
     k_rekey<<<grid_for(n), 256, 0, s>>>(phf, triplets, n, k, m, cells, bad, colliding);
+}
+
+void launch_rekey_alt(DevPhf const& phf, const uint8_t* triplets, uint64_t n, uint32_t* cells, unsigned long long* bad,
+                      cudaStream_t s) {
+    if (n) k_rekey_alt<<<grid_for(n), 256, 0, s>>>(phf, triplets, n, cells, bad);
+}
+void launch_split_alt(const uint32_t* cells, uint64_t n, uint8_t* p1, uint8_t* size, unsigned long long* unset,
+                      cudaStream_t s) {
+    if (n) k_split_alt<<<grid_for(n), 256, 0, s>>>(cells, n, p1, size, unset);
 }
 
 void launch_cell_counts(const uint32_t* cells, uint64_t n, InvCounts* blk, unsigned long long* unset, cudaStream_t s) {

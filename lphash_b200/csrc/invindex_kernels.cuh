@@ -24,6 +24,13 @@ struct InvCounts {  // of one block of cells, or a prefix of blocks
 void launch_rekey(DevPhf const& phf, const uint8_t* triplets, uint64_t n, uint32_t k, uint32_t m,
                   uint32_t* cells, unsigned long long* bad, unsigned long long* colliding, cudaStream_t s);
 
+// build-u (mphf_alt): cells[minimizer_order(itself)] = 0x80000000 | p1 | size << 8, then the two byte lists in
+// order (ref src/unpartitioned_mphf.cpp:78-96, 152-168); *unset counts cells never written
+void launch_rekey_alt(DevPhf const& phf, const uint8_t* triplets, uint64_t n, uint32_t* cells, unsigned long long* bad,
+                      cudaStream_t s);
+void launch_split_alt(const uint32_t* cells, uint64_t n, uint8_t* p1, uint8_t* size, unsigned long long* unset,
+                      cudaStream_t s);
+
 // per block of kInvBlock cells: counts by type; *unset += cells never written
 void launch_cell_counts(const uint32_t* cells, uint64_t n, InvCounts* blk, unsigned long long* unset, cudaStream_t s);
 // inclusive prefix over the blocks, in place

@@ -149,3 +149,15 @@ def build_inverted_index(triplets, orders, k, m):
     rs = len(lp)
     ns = rs + len(rc)
     return (kinds.count(MAXIMAL), rs, ns, ns + len(nsz)), body
+
+
+def build_inverted_index_alt(triplets, orders):
+    """build-u (lphash::mphf_alt): positions = Elias-Fano of the prefix sums of p1, sizes = of the sizes, both in
+    minimizer_order order (src/unpartitioned_mphf.cpp:78-96, 152-169).  Returns (num_kmers_in_main_index, image of
+    positions + image of sizes)."""
+    by_order = np.argsort(np.asarray(orders), kind="stable")
+    p1 = np.cumsum(triplets["p1"][by_order].astype(np.uint64))
+    size = np.cumsum(triplets["size"][by_order].astype(np.uint64))
+    body = ef_sequence_image(p1.tolist(), int(p1[-1]) if len(p1) else 0)
+    body += ef_sequence_image(size.tolist(), int(size[-1]) if len(size) else 0)
+    return (int(size[-1]) if len(size) else 0), body

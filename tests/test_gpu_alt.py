@@ -48,3 +48,26 @@ def test_partitioned_loader_rejects_an_unpartitioned_file():
     with pytest.raises(api.LphashError) as e:
         api.Mphf.load(os.path.join(GOLDEN_DIR, "alt_k31_m20_u64.lph"), g.bits)
     assert e.value.code == api.E_FORMAT
+
+
+@pytest.mark.parametrize("name,bits", [("k31_m20_u64", 64), ("k63_m24_u128", 128), ("k25_m13_u64", 64)])
+def test_build_u_part3_and_writer_reproduce_the_reference_file(name, bits):
+    """build-u on the GPU around the reference's two PTHash functions: scan + classify of the index contigs,
+    lphb_build_inverted_index_alt (positions + sizes), lphb_lph_assemble_alt - byte for byte the file the reference's
+    mphf_alt::build saved (src/unpartitioned_mphf.cpp:31-140)"""
+    import struct
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    image = open(os.path.join(GOLDEN_DIR, f"alt_{name}.lph"), "rb").read()
+    sec = api.lph_sections(image, bits, alt=True)
+    k, m, seed, nkmers, distinct, main = struct.unpack_from("<BBQQQQ", image, 0)
+    trip, ids, nk, _ = api.scan_classify(z["index_bases"], z["index_offsets"], k, m, seed)
+    assert nk == nkmers and len(trip) == distinct
+    mo = image[sec[0]:sec[1]]
+    info, body = api.build_inverted_index_alt(mo, trip)
+    assert info.num_kmers_in_main_index == main
+    assert body == image[sec[1]:sec[3]]
+    out = api.lph_assemble_alt(k, m, seed, nkmers, distinct, info, mo, body, image[sec[3]:sec[4]])
+    assert out == image
+    with pytest.raises(api.LphashError) as e:
+        api.build_inverted_index_alt(image[sec[3]:sec[4]], trip)  # the fallback function: other keys
+    assert e.value.code == api.E_ARG

@@ -123,3 +123,20 @@ def test_part3_restatement_on_synthetic_branches(name):
     ef = invindex.ef_sequence_image(np.cumsum(invindex.value_lists(trip, orders, k, m)).tolist(),
                                     int(invindex.value_lists(trip, orders, k, m).sum()))
     assert hashlib.sha256(ef).hexdigest() == str(z["ef_sha256"])
+
+
+@pytest.mark.parametrize("name,bits", [("k31_m20_u64", 64), ("k63_m24_u128", 128), ("k25_m13_u64", 64)])
+def test_part3_restatement_unpartitioned(name, bits):
+    """build-u: positions + sizes of the `.lph` the reference's mphf_alt::build saved (src/unpartitioned_mphf.cpp:78-96,
+    152-169)"""
+    import struct
+    from conftest import GOLDEN_DIR, load_golden
+    from oracle import invindex
+    image = open(os.path.join(GOLDEN_DIR, f"alt_{name}.lph"), "rb").read()
+    from lphash_b200 import api
+    sec = api.lph_sections(image, bits, alt=True)
+    trip = load_golden(name).triplets
+    orders = oracle.phf_positions(image[sec[0]:sec[1]], trip["itself"])
+    main, body = invindex.build_inverted_index_alt(trip, orders)
+    assert main == struct.unpack_from("<Q", image, 26)[0]
+    assert body == image[sec[1]:sec[3]]
