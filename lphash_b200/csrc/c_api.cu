@@ -42,6 +42,11 @@ struct Workspace {
     uint64_t h_counts_cap = 0;
     std::vector<cudaEvent_t> ev_cnt;         // per chunk: its run count has reached h_counts
     unsigned long long* h_status = nullptr;  // pinned, 4 words
+    // small batches (one record per call, as the reference's own loop makes them): one device block and its pinned
+    // mirror, so that a call is one copy up, the kernels, one copy down
+    DevBuf small;
+    unsigned char* h_small = nullptr;
+    static constexpr uint64_t kSmallBytes = uint64_t(1) << 20;
     cudaStream_t stream = nullptr;
     // chunk pipeline of lphb_query_stream: two extra streams so that the H2D copy of chunk j+1,
     // the kernels of chunk j and the D2H copy of chunk j-1 overlap (PCIe is full duplex)
@@ -86,8 +91,9 @@ struct Workspace {
         for (DevBuf* b : {&bases, &offsets, &code_off, &codes, &dirty, &status, &tmp, &aux0, &aux1,
                           &aux2, &aux3, &codes2, &tile, &r_start, &r_head, &r_rank, &r_head_at, &r_tmp, &r_runs, &r_count,
                           &q_bases, &q_flag, &q_voff, &q_vstart, &q_status, &q_tmp, &q_vcode_off, &q_dirty, &q_tile, &q_spur,
-                          &q_spur_cnt, &q_out_off, &q_out})
+                          &q_spur_cnt, &q_out_off, &q_out, &small})
             b->release();
+        if (h_small) cudaFreeHost(h_small);
         if (h_counts) cudaFreeHost(h_counts);
         for (cudaEvent_t e : ev_cnt) cudaEventDestroy(e);
         if (h_status) cudaFreeHost(h_status);
@@ -134,6 +140,7 @@ struct lphb_mphf {
     lphb_info info{};
     lphb_stats stats{};
     uint64_t last_dirty_n = 0;  // contigs of the last query call (length of the dirty-flag array)
+    const uint8_t* last_dirty = nullptr;  // where its flags are (device)
     Workspace ws;
 };
 
@@ -231,7 +238,12 @@ void run_kernels(lphb_mphf* f, DevBatch const& b, cudaStream_t s) {
     attach_l2_window(f, s);
     const int slot = int(f->ws.ev_next % Workspace::kEvRing);
     CK(cudaEventRecord(f->ws.ev0[slot], s));
-    if (!launch_query_tiled(f->img, b, s)) launch_query_generic(f->img, b, s);
+    // A batch of a few tiles would leave one or two warps of the tiled kernel to walk its whole (cold) code alone,
+    // about 40 us whatever the size; below 256 K bases the one-thread-per-k-mer kernel answers sooner (10 us for a
+    // record of 8,000 bases; tools/ubench/call_latency.cpp).  LPHB_GENERIC_BELOW overrides (tests: 0).
+    const char* gb = getenv("LPHB_GENERIC_BELOW");
+    const uint64_t generic_below = gb ? strtoull(gb, nullptr, 10) : (uint64_t(1) << 18);
+    if (b.end_base - b.first_base < generic_below || !launch_query_tiled(f->img, b, s)) launch_query_generic(f->img, b, s);
     CK(cudaEventRecord(f->ws.ev1[slot], s));
     ++f->ws.ev_next;
     ++f->ws.ev_pending;
@@ -355,7 +367,7 @@ int lphb_mphf_stats(const lphb_mphf* cf, lphb_stats* stats) {
 
 int lphb_mphf_dirty_flags(const lphb_mphf* f, const uint8_t** d_flags, uint64_t* n_contigs) {
     if (!f || !d_flags || !n_contigs) return fail(LPHB_E_ARG, "null argument");
-    *d_flags = f->ws.dirty.as<uint8_t>();
+    *d_flags = f->last_dirty ? f->last_dirty : f->ws.dirty.as<uint8_t>();
     *n_contigs = f->last_dirty_n;
     return LPHB_OK;
 }
@@ -497,6 +509,64 @@ int query_stream_host(lphb_mphf* f, const char* bases, const uint64_t* offsets, 
         const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
         if (span && !bases) return fail(LPHB_E_ARG, "bases is null");
         if (want_runs && total >= (1ull << 31)) return fail(LPHB_E_ARG, "batch holds >= 2^31 k-mers: split it");
+        f->last_dirty = nullptr;
+        // ---- small batch (the reference's own loop hands over one record per call, src/query.cpp:48-56): one
+        // device block [codes | status | dirty flags | offsets | code offsets | bases] with a pinned mirror - one
+        // copy up (status and flags arrive zeroed with it), the kernels, one copy down [codes | status].  A
+        // contig with non-ACGT bytes sends the call through the general path below.
+        {
+            const uint64_t codes_b = (total * 8 + 63) & ~uint64_t(63), dirty_b = (n_contigs + 8 + 63) & ~uint64_t(63);
+            const uint64_t off_b = (n_contigs + 1) * 8;
+            const uint64_t in_b = 64 + dirty_b + 2 * off_b + span + 64, all_b = codes_b + in_b;
+            if (!want_runs && codes && total && total <= codes_capacity && all_b <= Workspace::kSmallBytes &&
+                !getenv("LPHB_NO_SMALL_PATH")) {
+                if (!ws.h_small) {
+                    ws.small.reserve(Workspace::kSmallBytes);
+                    CK(cudaMallocHost(reinterpret_cast<void**>(&ws.h_small), Workspace::kSmallBytes));
+                }
+                unsigned char* h = ws.h_small;
+                auto* d = ws.small.as<unsigned char>();
+                const uint64_t at_status = codes_b, at_dirty = at_status + 64, at_off = at_dirty + dirty_b,
+                               at_coff = at_off + off_b, at_bases = at_coff + off_b;
+                std::memset(h + at_status, 0, 64 + dirty_b);
+                std::memcpy(h + at_off, offsets, off_b);
+                std::memcpy(h + at_coff, code_offsets, off_b);
+                if (span) std::memcpy(h + at_bases, bases + first, span);
+                std::memset(h + at_bases + span, 'A', 64);
+                ws.order_after_previous(s);
+                CK(cudaMemcpyAsync(d + at_status, h + at_status, in_b, cudaMemcpyHostToDevice, s));
+                if (sink.non_streaming) launch_sanitize(reinterpret_cast<char*>(d + at_bases), span, s);
+                DevBatch b{};
+                b.bases = reinterpret_cast<const char*>(d + at_bases) - first;
+                b.offsets = reinterpret_cast<const uint64_t*>(d + at_off);
+                b.code_off = reinterpret_cast<const uint64_t*>(d + at_coff);
+                b.n_contigs = n_contigs;
+                b.first_base = first;
+                b.end_base = first + span;
+                b.codes = reinterpret_cast<uint64_t*>(d);
+                b.dirty = d + at_dirty;
+                b.status = reinterpret_cast<unsigned long long*>(d + at_status);
+                ws.tile.reserve(query_tiled_ws_bytes(span));
+                b.tile_ws = ws.tile.p;
+                b.tile_ws_bytes = ws.tile.cap;
+                run_kernels(f, b, s);
+                ws.mark_last(s);
+                CK(cudaMemcpyAsync(h, d, codes_b + 64, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                CK(cudaGetLastError());
+                const auto* st = reinterpret_cast<const unsigned long long*>(h + at_status);
+                f->last_dirty_n = n_contigs;
+                f->last_dirty = d + at_dirty;
+                f->stats.h2d_bytes = in_b;
+                f->stats.d2h_bytes = codes_b + 64;
+                if (st[1] == 0) {
+                    std::memcpy(codes, h, total * 8);
+                    return LPHB_OK;
+                }
+                f->last_dirty = nullptr;  // non-ACGT bytes: start over on the general path
+                f->stats = lphb_stats{};
+            }
+        }
         ws.bases.reserve(span + 64);
         ws.offsets.reserve((n_contigs + 1) * 8);
         ws.code_off.reserve((n_contigs + 1) * 8);

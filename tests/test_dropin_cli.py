@@ -30,9 +30,16 @@ def need_binaries():
         pytest.skip("drop-in binaries not built (integration/dropin/build_dropin.sh needs the reference tree)")
 
 
+def cli_env(extra=None):
+    """the library's own defaults (the suite pins LPHB_GENERIC_BELOW for its in-process tests, conftest.py)"""
+    env = {k: v for k, v in os.environ.items() if k != "LPHB_GENERIC_BELOW"}
+    env.update(extra or {})
+    return env
+
+
 def run_query(cli, path):
     t0 = time.perf_counter()
-    r = subprocess.run([cli, "query-p", "-i", LPH, "-q", path], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([cli, "query-p", "-i", LPH, "-q", path], capture_output=True, text=True, timeout=900, env=cli_env())
     secs = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr
     f = r.stdout.strip().splitlines()[-1].split(",")
@@ -65,7 +72,7 @@ def test_query_p_on_a_file_with_non_acgt_bytes():
 def run_build(cli, src, k, m, out, tmp, extra=(), env=None):
     t0 = time.perf_counter()
     r = subprocess.run([cli, "build-p", "-i", src, "-k", str(k), "-m", str(m), "-o", out, "-d", tmp, *extra],
-                       capture_output=True, text=True, timeout=1800, env=env)
+                       capture_output=True, text=True, timeout=1800, env=cli_env(env))
     assert r.returncode == 0, r.stderr
     return r.stdout, r.stderr, time.perf_counter() - t0
 
@@ -97,7 +104,7 @@ def test_build_p_64_bit_flavour_and_cpu_switch(tmp_path):
             f.write(b">%d\n" % i + raw[int(off[i]):int(off[i + 1])] + b"\n")
     outs = {}
     for tag, cli, env in [("gpu", gpu64, None), ("ref", ref64, None),
-                          ("cpu_switch", gpu64, dict(os.environ, LPHASH_B200_CPU_BUILD="1"))]:
+                          ("cpu_switch", gpu64, {"LPHASH_B200_CPU_BUILD": "1"})]:
         out = str(tmp_path / (tag + ".lph"))
         csv, _, _ = run_build(cli, str(fa), 31, 20, out, str(tmp_path), env=env)
         outs[tag] = (csv, open(out, "rb").read())

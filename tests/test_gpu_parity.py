@@ -65,6 +65,38 @@ def test_single_contig_calls_match(golden, handles):
         assert np.array_equal(got, want), i
 
 
+@pytest.mark.parametrize("generic_below", [None, "0"])      # library default (generic kernel below 256 K bases) / tiled kernel
+@pytest.mark.parametrize("small_path", [True, False])        # one pinned block up, one down / the general path
+def test_one_record_per_call_paths(golden, handles, generic_below, small_path, monkeypatch):
+    """The reference's own loop hands over one record per call (src/query.cpp:48-56): every contig of the query batch
+    alone, streaming and non-streaming, through the small-batch path and the general one, on both kernels - clean
+    records, non-members, short and empty records, records with non-ACGT bytes (which leave the small path)."""
+    if generic_below is None:
+        monkeypatch.delenv("LPHB_GENERIC_BELOW", raising=False)
+    else:
+        monkeypatch.setenv("LPHB_GENERIC_BELOW", generic_below)
+    if not small_path:
+        monkeypatch.setenv("LPHB_NO_SMALL_PATH", "1")
+    f = handles(golden.name)
+    off = golden.q_code_offsets
+    contigs = golden.contigs()
+    clean = golden.is_clean()
+    picks = list(range(0, 16)) + list(range(len(contigs) - 70, len(contigs), 2))
+    for i in picks:
+        want = golden.q_codes[int(off[i]):int(off[i + 1])]
+        got = f(contigs[i])
+        assert np.array_equal(got, want), i
+        if clean[i] and len(contigs[i]) >= golden.k:  # same codes on ACGT-only input
+            assert np.array_equal(f(contigs[i], streaming=False), want), i
+    # a few records per call, offsets not starting at zero
+    raw = golden.q_bases
+    qoff = golden.q_offsets
+    sub = qoff[3:9]
+    codes, coff = f.query_batch(raw, sub)
+    assert np.array_equal(codes, golden.q_codes[int(off[3]):int(off[8])])
+    assert np.array_equal(coff, off[3:9] - off[3])
+
+
 def test_clean_batch_has_no_dirty_contigs_and_is_perfect(golden, handles):
     f = handles(golden.name)
     codes, code_off = f.query_batch(golden.index_bases, golden.index_offsets)
