@@ -494,3 +494,38 @@ def test_non_streaming_branch_matches_the_reference(name, handles):
     assert np.array_equal(np.diff(code_off).astype(np.int64), np.array([len(c) - g.k + 1 for c in contigs]))
     assert np.array_equal(codes, np.concatenate([r.query(c, streaming=False) for c in contigs]))
     r.close()
+
+
+@pytest.mark.parametrize("name", ["k31_m20_u64", "k31_m16_u128", "k63_m24_u128", "k47_m20_u128", "k15_m7_u64", "k21_m11_u64",
+                                  "k25_m13_u64"])
+def test_contig_seams_at_every_tile_alignment(name, handles):
+    """Contig lengths swept so that seams fall at every offset of a warp tile (992 / 960 / 928 starts) and of a
+    16-byte word: members (substrings of the index contigs), non-members, records shorter than k and than m, empty
+    records, lower case, a sprinkle of N - streaming query and build scan against the oracle."""
+    g = load_golden(name)
+    f = handles(name)
+    o = oracle.OracleMphf(g.lph, g.bits)
+    rng = np.random.default_rng(g.k * 1000 + g.m)
+    idx = g.index_bases
+    lens = list(range(0, 70)) + list(range(900, 1040, 3)) + list(range(1880, 2010, 7)) + [5000, 2977, 1, 0, 4093]
+    pieces = []
+    for i, L in enumerate(lens):
+        if i % 3 == 0 and L <= len(idx) - 1:
+            s0 = int(rng.integers(0, len(idx) - L))
+            p = idx[s0:s0 + L].copy()             # crosses index contig seams: members and non-members mixed
+        else:
+            p = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L)
+        if i % 11 == 5 and L > 3:
+            p[rng.integers(0, L, size=2)] = ord("N")
+        if i % 7 == 2:
+            p = np.frombuffer(p.tobytes().lower(), dtype=np.uint8)
+        pieces.append(p)
+    bases = np.concatenate(pieces).astype(np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in pieces])]).astype(np.uint64)
+    want, want_off = o.query_batch(bases, offsets)
+    got, got_off = f.query_batch(bases, offsets)
+    assert np.array_equal(got_off, want_off)
+    assert np.array_equal(got, want)
+    rec_w, nk_w, mm_w = oracle.scan(bases, offsets, g.k, g.m, mode=0)
+    rec, nk, mm = api.scan_superkmers(bases, offsets, g.k, g.m)
+    assert (nk, mm) == (nk_w, mm_w) and np.array_equal(rec, rec_w)
