@@ -108,6 +108,20 @@ public:
         lphb_mphf_info(h_, &info_);
     }
 
+    // the unpartitioned variant (lphash::mphf_alt, build-u / query-u): same handle, same queries
+    void load_alt(const char* filename, int device = 0) {
+        reset();
+        int rc = lphb_mphf_alt_load_file(filename, kmer_bits, device, &h_);
+        if (rc != LPHB_OK) detail::raise("lphash_b200::mphf::load_alt", rc);
+        lphb_mphf_info(h_, &info_);
+    }
+    void load_alt(const void* image, uint64_t nbytes, int device = 0) {
+        reset();
+        int rc = lphb_mphf_alt_load_memory(image, nbytes, kmer_bits, device, &h_);
+        if (rc != LPHB_OK) detail::raise("lphash_b200::mphf::load_alt", rc);
+        lphb_mphf_info(h_, &info_);
+    }
+
     uint64_t get_minimizer_L0() const noexcept { return info_.distinct_minimizers; }
     uint64_t get_kmer_count() const noexcept { return info_.nkmers; }
     uint32_t get_k() const noexcept { return info_.k; }

@@ -28,9 +28,12 @@ build_flavour() {
   echo "typedef $type kmer_t;" > "$tmp/include/compile_constants.tpd"
   mv "$tmp/include/partitioned_mphf.hpp" "$tmp/include/partitioned_mphf_reference.hpp"   # the original, untouched
   cp "$HERE/partitioned_mphf.hpp" "$tmp/include/partitioned_mphf.hpp"                      # the shadow
+  mv "$tmp/include/unpartitioned_mphf.hpp" "$tmp/include/unpartitioned_mphf_reference.hpp"
+  cp "$HERE/unpartitioned_mphf.hpp" "$tmp/include/unpartitioned_mphf.hpp"
+  cp "$HERE/gpu_build.hpp" "$tmp/include/gpu_build.hpp"
   ( cd "$tmp"
     for f in $REF_TUS; do   # the reference's own translation units: `mphf` is the renamed reference class
-      g++ $CXXFLAGS -DLPHASH_B200_REFERENCE_TU -Dmphf=mphf_reference -I"$ROOT/include" -c "$f" -o "$(basename "$f" .cpp).o" &
+      g++ $CXXFLAGS -DLPHASH_B200_REFERENCE_TU -Dmphf=mphf_reference -Dmphf_alt=mphf_alt_reference -I"$ROOT/include" -c "$f" -o "$(basename "$f" .cpp).o" &
     done
     # the driver, unmodified: its `mphf` is the GPU-backed class of the shadow header
     g++ $CXXFLAGS -DLPHASH_B200_KMER_BITS="$bits" -DLPHASH_B200_WITH_ZLIB -I"$ROOT/include" -c src/lphash.cpp -o lphash.o &

@@ -110,3 +110,36 @@ def test_build_p_64_bit_flavour_and_cpu_switch(tmp_path):
         outs[tag] = (csv, open(out, "rb").read())
     assert outs["gpu"] == outs["ref"] == outs["cpu_switch"]
     assert outs["gpu"][1] == open(os.path.join(GOLDEN_DIR, "k31_m20_u64.lph"), "rb").read()
+
+
+def test_build_u_and_query_u_through_the_gpu_classes(tmp_path):
+    """the unpartitioned twin: `build-u` on the GPU writes the reference CLI's file and CSV line and passes --check;
+    `query-u` counts the same k-mers"""
+    gpu64, ref64 = GPU_CLI.replace("128", "64"), REF_CLI.replace("128", "64")
+    if not (os.path.exists(gpu64) and os.path.exists(ref64)):
+        pytest.skip("64-bit drop-in binaries not built")
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN_DIR, "k31_m20_u64.npz"))
+    raw, off = z["index_bases"].tobytes(), z["index_offsets"]
+    fa = tmp_path / "index.fa"
+    with open(fa, "wb") as f:
+        for i in range(len(off) - 1):
+            f.write(b">%d\n" % i + raw[int(off[i]):int(off[i + 1])] + b"\n")
+    outs = {}
+    for tag, cli, extra in [("gpu", gpu64, ["--check"]), ("ref", ref64, [])]:
+        out = str(tmp_path / (tag + ".lph"))
+        r = subprocess.run([cli, "build-u", "-i", str(fa), "-k", "31", "-m", "20", "-o", out, "-d", str(tmp_path), *extra],
+                           capture_output=True, text=True, timeout=900, env=cli_env())
+        assert r.returncode == 0, r.stderr
+        if extra:
+            assert "Everything is ok" in r.stderr, r.stderr[-2000:]
+        outs[tag] = (r.stdout, open(out, "rb").read())
+    assert outs["gpu"] == outs["ref"]
+    assert outs["gpu"][1] == open(os.path.join(GOLDEN_DIR, "alt_k31_m20_u64.lph"), "rb").read()
+    counts = []
+    for cli in (gpu64, ref64):
+        r = subprocess.run([cli, "query-u", "-i", str(tmp_path / "gpu.lph"), "-q", str(fa)], capture_output=True, text=True,
+                           timeout=900, env=cli_env())
+        assert r.returncode == 0, r.stderr
+        counts.append(int(r.stdout.strip().splitlines()[-1].split(",")[2]))
+    assert counts[0] == counts[1] == int(z["n_kmers"])
