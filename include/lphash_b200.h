@@ -140,6 +140,10 @@ int lphb_query_stream_device(lphb_mphf* f, const char* d_bases, const uint64_t* 
                              uint64_t codes_capacity, uint64_t* d_code_offsets,
                              uint64_t* d_status, void* stream);
 
+/* Diagnostic: the flat device image behind the handle (layout: lphash_b200/csrc/device_image.h), e.g. to compare
+ * the GPU-side decode of a load with the host-side one (LPHB_HOST_DECODE=1).  Read it with lphb_copy_to_host.  */
+int lphb_mphf_device_image(const lphb_mphf* f, const void** d_image, uint64_t* nbytes);
+
 /* Per-contig flags of the last query call on the handle: *d_flags = DEVICE pointer to *n_contigs
  * bytes, nonzero where the contig contains a non-ACGT byte; valid (in stream order) until the next
  * query call on the handle.                                                                        */

@@ -67,7 +67,7 @@ EXPORTS = ["lphb_last_error", "lphb_version", "lphb_device_count", "lphb_mphf_lo
            "lphb_scan_superkmers_device", "lphb_copy_to_host", "lphb_query_nonstreaming",
            "lphb_mphf_alt_load_file", "lphb_mphf_alt_load_memory", "lphb_inverted_index_bound",
            "lphb_build_inverted_index", "lphb_lph_assemble", "lphb_lph_sections", "lphb_build_inverted_index_alt",
-           "lphb_lph_assemble_alt"]
+           "lphb_lph_assemble_alt", "lphb_mphf_device_image"]
 
 _lib = None
 
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
                                      C.POINTER(u64), p, u64, C.POINTER(u64), C.POINTER(u64)]
     L.lphb_copy_to_host.argtypes = [i32, p, p, u64]
     L.lphb_host_alloc.argtypes = [C.POINTER(p), u64]
+    L.lphb_mphf_device_image.argtypes = [p, C.POINTER(p), C.POINTER(u64)]
     L.lphb_inverted_index_bound.argtypes = [u64]
     L.lphb_inverted_index_bound.restype = u64
     L.lphb_build_inverted_index.argtypes = [i32, C.c_uint32, C.c_uint32, p, u64, p, u64, p, u64, C.POINTER(u64),
@@ -196,6 +197,14 @@ class Mphf:
 
     def get_minimizer_L0(self) -> int:
         return self.info.distinct_minimizers
+
+    def device_image(self) -> bytes:
+        """the flat device image behind the handle, copied to the host (diagnostic)"""
+        ptr, n = C.c_void_p(), C.c_uint64(0)
+        _check(lib().lphb_mphf_device_image(self._h, C.byref(ptr), C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint8)
+        _check(lib().lphb_copy_to_host(self.info.device, out.ctypes.data, ptr, n.value))
+        return out.tobytes()
 
     def stats(self) -> Stats:
         s = Stats()

@@ -375,10 +375,8 @@ int lphb_lph_assemble_alt(uint32_t k, uint32_t m, uint64_t mm_seed, uint64_t nkm
 int lphb_lph_sections(const void* image, uint64_t nbytes, int kmer_bits, int alt, uint64_t sections[5]) {
     if (!image || !sections) return fail(LPHB_E_ARG, "null argument");
     return guarded([&]() -> int {
-        ImageBuilder b;
-        if (alt) b.parse_alt(static_cast<const uint8_t*>(image), nbytes, kmer_bits);
-        else b.parse(static_cast<const uint8_t*>(image), nbytes, kmer_bits);
-        for (int i = 0; i < 5; ++i) sections[i] = b.sections()[i];
+        const ImagePlan plan = ImageBuilder::plan(static_cast<const uint8_t*>(image), nbytes, kmer_bits, alt != 0);
+        for (int i = 0; i < 5; ++i) sections[i] = plan.sections[i];
         return LPHB_OK;
     });
 }

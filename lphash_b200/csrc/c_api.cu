@@ -18,6 +18,7 @@
 
 #include "../../include/lphash_b200.h"
 #include "api_internal.h"
+#include "image_decode.cuh"
 #include "lph_image.h"
 #include "query_kernels.cuh"
 #include "scan_kernels.cuh"
@@ -150,23 +151,47 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
     if (!out) return fail(LPHB_E_ARG, "out is null");
     *out = nullptr;
     return guarded([&]() -> int {
+        // The structure of the file is walked on the host (sizes, ranges: format errors surface before any CUDA
+        // call); the decoding - compact vectors, Elias-Fano, wavelet-tree ranks, one word per bucket - runs on the
+        // GPU (image_decode.cu).  LPHB_HOST_DECODE=1 decodes on the host instead (lph_image.cpp; tests compare the
+        // two images byte for byte), and so does a machine without a usable device, so that a malformed file is
+        // reported as such before the missing device is.
         ImageBuilder builder;
+        ImagePlan plan;
         const auto t_parse0 = std::chrono::steady_clock::now();
-        if (alt) builder.parse_alt(data, n, kmer_bits);
-        else builder.parse(data, n, kmer_bits);  // host-only: format errors surface before any CUDA call
-        const auto t_parse1 = std::chrono::steady_clock::now();
         int count = 0;
-        CK(cudaGetDeviceCount(&count));
-        if (device < 0 || device >= count) return fail(LPHB_E_CUDA, "no such CUDA device");
+        const bool have_device = cudaGetDeviceCount(&count) == cudaSuccess && device >= 0 && device < count;
+        if (!have_device) cudaGetLastError();
+        const char* hd = getenv("LPHB_HOST_DECODE");
+        const bool host_decode = !have_device || (hd && hd[0] && hd[0] != '0');
+        if (host_decode) {
+            if (alt) builder.parse_alt(data, n, kmer_bits);
+            else builder.parse(data, n, kmer_bits);
+        } else {
+            plan = ImageBuilder::plan(data, n, kmer_bits, alt);
+        }
+        const auto t_parse1 = std::chrono::steady_clock::now();
+        if (!have_device) return fail(LPHB_E_CUDA, "no such CUDA device");
         DeviceGuard g(device);
         auto* f = new lphb_mphf();
         try {
             f->device = device;
-            auto const& arena = builder.arena();
-            CK(cudaMalloc(&f->d_arena, arena.size() + 256));
-            CK(cudaMemcpy(f->d_arena, arena.data(), arena.size(), cudaMemcpyHostToDevice));
-            f->img = builder.rebased(f->d_arena);
-            f->arena_bytes = arena.size();
+            const uint64_t arena_bytes = host_decode ? builder.arena().size() : plan.arena_bytes;
+            CK(cudaMalloc(&f->d_arena, arena_bytes + 256));
+            if (host_decode) {
+                CK(cudaMemcpy(f->d_arena, builder.arena().data(), arena_bytes, cudaMemcpyHostToDevice));
+                f->img = builder.rebased(f->d_arena);
+            } else {
+                uint64_t collision_base = 0;
+                decode_image_on_device(plan, f->d_arena, &collision_base);
+                f->img = rebase_image(plan.img, f->d_arena);
+                f->img.collision_base = collision_base;
+            }
+            f->arena_bytes = arena_bytes;
+            struct ArenaView {
+                uint64_t n;
+                uint64_t size() const { return n; }
+            } arena{arena_bytes};
             f->info.load_host_ms = std::chrono::duration<double, std::milli>(t_parse1 - t_parse0).count();
             f->info.load_h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parse1).count();
             {
@@ -201,8 +226,8 @@ int load_image(const uint8_t* data, uint64_t n, int kmer_bits, int device, lphb_
             i.right_coll_sizes_start = f->img.right_start;
             i.none_sizes_start = f->img.none_sizes_start;
             i.none_pos_start = f->img.none_pos_start;
-            i.fallback_keys = builder.fallback_keys();
-            i.file_bytes = builder.file_bytes();
+            i.fallback_keys = host_decode ? builder.fallback_keys() : plan.fallback_keys;
+            i.file_bytes = host_decode ? builder.file_bytes() : plan.file_bytes;
             i.device_bytes = arena.size();
         } catch (...) {
             f->ws.destroy();
@@ -362,6 +387,13 @@ int lphb_mphf_stats(const lphb_mphf* cf, lphb_stats* stats) {
         ws.ev_pending = 0;
     }
     *stats = f->stats;
+    return LPHB_OK;
+}
+
+int lphb_mphf_device_image(const lphb_mphf* f, const void** d_image, uint64_t* nbytes) {
+    if (!f || !d_image || !nbytes) return fail(LPHB_E_ARG, "null argument");
+    *d_image = f->d_arena;
+    *nbytes = f->arena_bytes;
     return LPHB_OK;
 }
 

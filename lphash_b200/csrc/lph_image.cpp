@@ -473,6 +473,143 @@ void ImageBuilder::parse_phf(const uint8_t* data, uint64_t n) {
     arena_.resize((arena_.size() + 255) & ~uint64_t(255), 0);
 }
 
+// ---- structure walk for the device-side loader -------------------------------------------------------------------
+namespace {
+struct Layout {  // the arena offsets ImageBuilder::append would hand out
+    uint64_t size = 0;
+    uint64_t take(uint64_t bytes) {
+        const uint64_t off = (size + 255) & ~uint64_t(255);
+        size = off + bytes;
+        return off;
+    }
+};
+}  // namespace
+
+ImagePlan ImageBuilder::plan(const uint8_t* data, uint64_t n, int kmer_bits, bool alt) {
+    if (kmer_bits != 64 && kmer_bits != 128) throw FormatError("kmer_bits must be 64 or 128");
+    ImagePlan P;
+    P.alt = alt;
+    DevImage& img = P.img;
+    Cursor c{data, data + n};
+    img.k = c.pod<uint8_t>();
+    img.m = c.pod<uint8_t>();
+    img.kmer_bits = uint32_t(kmer_bits);
+    img.mm_seed = c.pod<uint64_t>();
+    img.nkmers = c.pod<uint64_t>();
+    img.distinct_minimizers = c.pod<uint64_t>();
+    uint64_t main_kmers = 0;
+    if (alt) {
+        main_kmers = c.pod<uint64_t>();
+    } else {
+        img.n_maximal = c.pod<uint64_t>();
+        img.right_start = c.pod<uint64_t>();
+        img.none_sizes_start = c.pod<uint64_t>();
+        img.none_pos_start = c.pod<uint64_t>();
+    }
+    if (img.m == 0 || img.m > 31 || img.k < img.m || img.k > uint32_t(kmer_bits / 2 - 1))
+        throw FormatError("k/m out of range for this kmer_t");
+    img.w = img.k - img.m + 1;
+    auto compact = [&](CompactRef& r) {
+        FileCompact f = c.compact();
+        r.size = f.size;
+        r.width = f.width;
+        r.words = VecRef{f.words, f.nwords};
+    };
+    auto ef = [&](EfRef& r) {
+        r.nbits = c.pod<uint64_t>();
+        r.high.p = c.vec<uint64_t>(r.high.n);
+        if ((r.nbits + 63) / 64 > r.high.n) throw FormatError("EF high bits shorter than declared");
+        r.positions = c.pod<uint64_t>();
+        uint64_t nb, ns, no;
+        c.vec<int64_t>(nb);
+        c.vec<uint16_t>(ns);
+        c.vec<uint64_t>(no);
+        compact(r.low);
+        if (r.low.size != r.positions) throw FormatError("EF: darray positions != number of values");
+    };
+    auto bits = [&](BitsRef& r) {
+        r.nbits = c.pod<uint64_t>();
+        r.words.p = c.vec<uint64_t>(r.words.n);
+        uint64_t np, nh;
+        c.vec<uint64_t>(np);
+        c.vec<uint64_t>(nh);
+        if ((r.nbits + 63) / 64 > r.words.n) throw FormatError("bit vector shorter than declared");
+    };
+    auto phf = [&](PhfRef& r, DevPhf& out) {
+        out.seed = c.pod<uint64_t>();
+        out.num_keys = c.pod<uint64_t>();
+        out.table_size = c.pod<uint64_t>();
+        c.pod<unsigned __int128>();
+        out.dense = c.pod<uint64_t>();
+        out.sparse = c.pod<uint64_t>();
+        c.pod<unsigned __int128>();
+        c.pod<unsigned __int128>();
+        compact(r.front_ranks);
+        compact(r.front_dict);
+        compact(r.back_ranks);
+        compact(r.back_dict);
+        r.n_buckets = r.front_ranks.size + r.back_ranks.size;
+        if (r.n_buckets != out.dense + out.sparse) throw FormatError("pilot count != bucket count");
+        if (out.table_size == 0 || out.table_size < out.num_keys) throw FormatError("single_phf: bad table size");
+        if (out.dense == 0 || out.sparse == 0) throw FormatError("single_phf: empty bucket class");
+        if (out.table_size >= (1ull << 31) || out.dense >= (1ull << 31) || out.sparse >= (1ull << 31))
+            throw FormatError("single_phf: table larger than 2^31 (impossible with 64-bit PTHash hashes)");
+        reciprocal64(out.table_size, out.m_table);
+        reciprocal64(out.dense, out.m_dense);
+        reciprocal64(out.sparse, out.m_sparse);
+        ef(r.free_slots);
+        r.n_free = out.table_size - out.num_keys;
+        if (r.free_slots.positions != r.n_free) throw FormatError("single_phf: free-slot count mismatch");
+    };
+    P.sections[0] = uint64_t(c.p - data);
+    phf(P.minimizer_order, img.minimizer_order);
+    P.sections[1] = uint64_t(c.p - data);
+    if (alt) {
+        ef(P.positions);
+        P.sections[2] = uint64_t(c.p - data);
+        ef(P.sizes);
+    } else {
+        bits(P.root);
+        bits(P.left_right);
+        bits(P.max_none);
+        P.sections[2] = uint64_t(c.p - data);
+        ef(P.sizes_and_positions);
+    }
+    P.sections[3] = uint64_t(c.p - data);
+    phf(P.fallback, img.fallback);
+    P.sections[4] = uint64_t(c.p - data);
+    if (c.p != c.end) throw FormatError("trailing bytes after the .lph image");
+    const uint64_t D = img.distinct_minimizers;
+    if (img.minimizer_order.num_keys != D) throw FormatError("inconsistent minimizer counts");
+    if (alt) {
+        if (P.positions.positions != D + 1 || P.sizes.positions != D + 1) throw FormatError("inconsistent minimizer counts");
+        img.collision_base = main_kmers;
+    } else {
+        if (P.root.nbits != D || P.left_right.nbits + P.max_none.nbits != D) throw FormatError("inconsistent minimizer counts");
+        if (!(img.right_start <= img.none_sizes_start && img.none_sizes_start <= img.none_pos_start &&
+              img.none_pos_start < P.sizes_and_positions.positions))
+            throw FormatError("inconsistent sizes_and_positions partition");
+    }
+    // the arena layout of parse / parse_alt: mo.pilot_hash, mo.free32, fb.pilot_hash, fb.free32, bucket table
+    Layout L;
+    auto place_phf = [&](PhfRef const& r, DevPhf& out) {
+        out.pilot_hash = reinterpret_cast<const uint64_t*>(uintptr_t(L.take((r.n_buckets + 2) * 8)));
+        out.free32 = reinterpret_cast<const uint32_t*>(uintptr_t(L.take((r.n_free + 4) * 4)));
+    };
+    place_phf(P.minimizer_order, img.minimizer_order);
+    place_phf(P.fallback, img.fallback);
+    const char* fw = getenv("LPHB_FORCE_WIDE_BUCKETS");
+    const bool wide = (fw && fw[0] && fw[0] != '0') || img.nkmers + 256 >= (1ull << 30);
+    const uint64_t T = D + P.minimizer_order.n_free;
+    img.buckets.n = T;
+    img.buckets.wide = wide ? 1 : 0;
+    img.buckets.entries = reinterpret_cast<const void*>(uintptr_t(L.take(wide ? (T + 4) * 8 : (T + 8) * 4)));
+    P.arena_bytes = (L.size + 255) & ~uint64_t(255);
+    P.fallback_keys = img.fallback.num_keys;
+    P.file_bytes = n;
+    return P;
+}
+
 DevImage ImageBuilder::rebased(const void* device_base) const {
     DevImage d = img_;
     auto* base = static_cast<const uint8_t*>(device_base);

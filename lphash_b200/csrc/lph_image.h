@@ -23,6 +23,44 @@ struct FormatError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// ---- what a serialized index consists of, as references into the file buffer (nothing decoded) ----------------
+// The device-side loader (image_decode.cu) uploads these pieces and evaluates compact_vector::access, the Elias-Fano
+// select / access, rs_bit_vector::rank and quartet_wtree::rank_of on the GPU; ImageBuilder::plan only walks the
+// structure and checks what can be checked from sizes alone.
+struct VecRef {      // a vector of 8-byte words inside the file (possibly unaligned there)
+    const uint8_t* p = nullptr;
+    uint64_t n = 0;
+};
+struct CompactRef {  // pthash::compact_vector
+    uint64_t size = 0, width = 0;
+    VecRef words;
+};
+struct EfRef {       // {bit_vector high; darray1 (skipped); compact_vector low}
+    uint64_t nbits = 0, positions = 0;
+    VecRef high;
+    CompactRef low;
+};
+struct BitsRef {     // rs_bit_vector (rank directory skipped)
+    uint64_t nbits = 0;
+    VecRef words;
+};
+struct PhfRef {      // pthash::single_phf<*, dictionary_dictionary, true>
+    CompactRef front_ranks, front_dict, back_ranks, back_dict;
+    EfRef free_slots;
+    uint64_t n_buckets = 0, n_free = 0;
+};
+struct ImagePlan {
+    bool alt = false;
+    DevImage img{};           // header fields, reciprocals; array pointers = byte offsets inside the arena
+    uint64_t arena_bytes = 0;
+    PhfRef minimizer_order, fallback;
+    BitsRef root, left_right, max_none;  // partitioned
+    EfRef sizes_and_positions;           // partitioned
+    EfRef positions, sizes;              // mphf_alt
+    uint64_t fallback_keys = 0, file_bytes = 0;
+    uint64_t sections[5] = {0, 0, 0, 0, 0};  // as ImageBuilder::sections()
+};
+
 // Arena under construction: every array is appended 256-byte aligned; device pointers in the
 // DevImage are stored as byte offsets first and rebased once the arena is on the device.
 class ImageBuilder {
@@ -36,6 +74,9 @@ public:
     //   hval = sizes[i] + positions.diff(i) - p, or num_kmers_in_main_index + fallback(kmer) when the size is 0)
     //   fits the same per-bucket word, so the device image and every kernel are shared with the partitioned form.
     void parse_alt(const uint8_t* data, uint64_t n, int kmer_bits);
+    // Structure walk only (see ImagePlan): the same checks on sizes and ranges as parse / parse_alt, the same arena
+    // layout, no decoding.  The references point into `data`, which must outlive the plan.
+    static ImagePlan plan(const uint8_t* data, uint64_t n, int kmer_bits, bool alt);
     // A serialized pthash::single_phf on its own (what build-p Part 3 evaluates, ref src/partitioned_mphf.cpp:
     // 96-100): afterwards the image holds `minimizer_order` only, free slots included.
     void parse_phf(const uint8_t* data, uint64_t n);
