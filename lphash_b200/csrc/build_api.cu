@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "api_internal.h"
+#include "image_decode.cuh"
 #include "invindex_kernels.cuh"
 
 using namespace lphb;
@@ -156,8 +157,7 @@ int lphb_build_inverted_index(int device, uint32_t k, uint32_t m, const void* mi
         return fail(LPHB_E_ARG, "null argument");
     if (m == 0 || k < m || k - m + 1 > 255) return fail(LPHB_E_ARG, "k/m out of range");
     return guarded([&]() -> int {
-        ImageBuilder phf_image;
-        phf_image.parse_phf(static_cast<const uint8_t*>(minimizer_order), minimizer_order_bytes);
+        const ImagePlan phf_plan = ImageBuilder::plan_phf(static_cast<const uint8_t*>(minimizer_order), minimizer_order_bytes);
         int count = 0;
         CK(cudaGetDeviceCount(&count));
         if (device < 0 || device >= count) return fail(LPHB_E_CUDA, "no such CUDA device");
@@ -173,10 +173,9 @@ int lphb_build_inverted_index(int device, uint32_t k, uint32_t m, const void* mi
         };
         try {
             cudaStream_t s = nullptr;  // the call is synchronous; the legacy stream orders it against the copies
-            auto const& arena = phf_image.arena();
-            d_arena.reserve(arena.size() + 256);
-            CK(cudaMemcpy(d_arena.p, arena.data(), arena.size(), cudaMemcpyHostToDevice));
-            const DevPhf phf = phf_image.rebased(d_arena.p).minimizer_order;
+            d_arena.reserve(phf_plan.arena_bytes + 256);
+            decode_phf_on_device(phf_plan, d_arena.p);  // pilots and free slots decoded on the GPU (image_decode.cu)
+            const DevPhf phf = rebase_image(phf_plan.img, d_arena.p).minimizer_order;
             if (phf.num_keys != n) return (cleanup(), fail(LPHB_E_ARG, "minimizer_order was built on a different number of keys"));
             d_trip.reserve(10 * n + 16);
             if (n) CK(cudaMemcpy(d_trip.p, triplets, 10 * n, cudaMemcpyHostToDevice));
@@ -276,8 +275,7 @@ int lphb_build_inverted_index_alt(int device, const void* minimizer_order, uint6
     if (!minimizer_order || (!triplets && n) || !out_bytes || !info || (!out && out_capacity))
         return fail(LPHB_E_ARG, "null argument");
     return guarded([&]() -> int {
-        ImageBuilder phf_image;
-        phf_image.parse_phf(static_cast<const uint8_t*>(minimizer_order), minimizer_order_bytes);
+        const ImagePlan phf_plan = ImageBuilder::plan_phf(static_cast<const uint8_t*>(minimizer_order), minimizer_order_bytes);
         int count = 0;
         CK(cudaGetDeviceCount(&count));
         if (device < 0 || device >= count) return fail(LPHB_E_CUDA, "no such CUDA device");
@@ -292,10 +290,9 @@ int lphb_build_inverted_index_alt(int device, const void* minimizer_order, uint6
         };
         try {
             cudaStream_t s = nullptr;
-            auto const& arena = phf_image.arena();
-            d_arena.reserve(arena.size() + 256);
-            CK(cudaMemcpy(d_arena.p, arena.data(), arena.size(), cudaMemcpyHostToDevice));
-            const DevPhf phf = phf_image.rebased(d_arena.p).minimizer_order;
+            d_arena.reserve(phf_plan.arena_bytes + 256);
+            decode_phf_on_device(phf_plan, d_arena.p);  // pilots and free slots decoded on the GPU (image_decode.cu)
+            const DevPhf phf = rebase_image(phf_plan.img, d_arena.p).minimizer_order;
             if (phf.num_keys != n) return (cleanup(), fail(LPHB_E_ARG, "minimizer_order was built on a different number of keys"));
             d_trip.reserve(10 * n + 16);
             if (n) CK(cudaMemcpy(d_trip.p, triplets, 10 * n, cudaMemcpyHostToDevice));

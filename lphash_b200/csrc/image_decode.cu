@@ -292,6 +292,24 @@ DevImage rebase_image(DevImage d, const void* device_base) {
     return d;
 }
 
+void decode_phf_on_device(ImagePlan const& P, void* d_arena) {
+    cudaStream_t s = nullptr;
+    Scratch sc;
+    auto* arena = static_cast<uint8_t*>(d_arena);
+    CK(cudaMemsetAsync(arena, 0, P.arena_bytes, s));
+    unsigned* err = sc.alloc<unsigned>(kNumErrors + 2);
+    CK(cudaMemsetAsync(err, 0, (kNumErrors + 2) * sizeof(unsigned), s));
+    const size_t tmp_bytes = scan_tmp_bytes(P.minimizer_order.free_slots.high.n + 1);
+    void* tmp = sc.alloc<uint8_t>(tmp_bytes);
+    phf_on_device(sc, P.minimizer_order, P.img.minimizer_order, arena, tmp, tmp_bytes, err, s);
+    unsigned h_err[kNumErrors] = {};
+    CK(cudaMemcpyAsync(h_err, err, sizeof h_err, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (int i = 0; i < kNumErrors; ++i)
+        if (h_err[i]) throw FormatError(kErrorText[i]);
+}
+
 void decode_image_on_device(ImagePlan const& P, void* d_arena, uint64_t* collision_base) {
     cudaStream_t s = nullptr;
     Scratch sc;

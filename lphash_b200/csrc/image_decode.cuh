@@ -18,6 +18,9 @@ namespace lphb {
 // Sets *collision_base for the partitioned form (needs one decoded value).
 void decode_image_on_device(ImagePlan const& plan, void* d_arena, uint64_t* collision_base);
 
+// The same for a plan of ImageBuilder::plan_phf: pilot_hash and free32 of plan.img.minimizer_order.
+void decode_phf_on_device(ImagePlan const& plan, void* d_arena);
+
 DevImage rebase_image(DevImage img, const void* device_base);
 
 }  // namespace lphb

@@ -485,6 +485,65 @@ struct Layout {  // the arena offsets ImageBuilder::append would hand out
 };
 }  // namespace
 
+void ImageBuilder::walk_compact(Cursor& c, CompactRef& r) {
+    FileCompact f = c.compact();
+    r.size = f.size;
+    r.width = f.width;
+    r.words = VecRef{f.words, f.nwords};
+}
+void ImageBuilder::walk_ef(Cursor& c, EfRef& r) {
+    r.nbits = c.pod<uint64_t>();
+    r.high.p = c.vec<uint64_t>(r.high.n);
+    if ((r.nbits + 63) / 64 > r.high.n) throw FormatError("EF high bits shorter than declared");
+    r.positions = c.pod<uint64_t>();
+    uint64_t nb, ns, no;
+    c.vec<int64_t>(nb);
+    c.vec<uint16_t>(ns);
+    c.vec<uint64_t>(no);
+    walk_compact(c, r.low);
+    if (r.low.size != r.positions) throw FormatError("EF: darray positions != number of values");
+}
+void ImageBuilder::walk_phf(Cursor& c, PhfRef& r, DevPhf& out) {
+    out.seed = c.pod<uint64_t>();
+    out.num_keys = c.pod<uint64_t>();
+    out.table_size = c.pod<uint64_t>();
+    c.pod<unsigned __int128>();
+    out.dense = c.pod<uint64_t>();
+    out.sparse = c.pod<uint64_t>();
+    c.pod<unsigned __int128>();
+    c.pod<unsigned __int128>();
+    walk_compact(c, r.front_ranks);
+    walk_compact(c, r.front_dict);
+    walk_compact(c, r.back_ranks);
+    walk_compact(c, r.back_dict);
+    r.n_buckets = r.front_ranks.size + r.back_ranks.size;
+    if (r.n_buckets != out.dense + out.sparse) throw FormatError("pilot count != bucket count");
+    if (out.table_size == 0 || out.table_size < out.num_keys) throw FormatError("single_phf: bad table size");
+    if (out.dense == 0 || out.sparse == 0) throw FormatError("single_phf: empty bucket class");
+    if (out.table_size >= (1ull << 31) || out.dense >= (1ull << 31) || out.sparse >= (1ull << 31))
+        throw FormatError("single_phf: table larger than 2^31 (impossible with 64-bit PTHash hashes)");
+    reciprocal64(out.table_size, out.m_table);
+    reciprocal64(out.dense, out.m_dense);
+    reciprocal64(out.sparse, out.m_sparse);
+    walk_ef(c, r.free_slots);
+    r.n_free = out.table_size - out.num_keys;
+    if (r.free_slots.positions != r.n_free) throw FormatError("single_phf: free-slot count mismatch");
+}
+
+ImagePlan ImageBuilder::plan_phf(const uint8_t* data, uint64_t n) {
+    // a serialized single_phf on its own: wrap it in a throw-away plan (walk_phf below is shared with plan())
+    ImagePlan P;
+    Cursor c{data, data + n};
+    walk_phf(c, P.minimizer_order, P.img.minimizer_order);
+    if (c.p != c.end) throw FormatError("trailing bytes after the serialized single_phf");
+    Layout L;
+    P.img.minimizer_order.pilot_hash = reinterpret_cast<const uint64_t*>(uintptr_t(L.take((P.minimizer_order.n_buckets + 2) * 8)));
+    P.img.minimizer_order.free32 = reinterpret_cast<const uint32_t*>(uintptr_t(L.take((P.minimizer_order.n_free + 4) * 4)));
+    P.arena_bytes = (L.size + 255) & ~uint64_t(255);
+    P.file_bytes = n;
+    return P;
+}
+
 ImagePlan ImageBuilder::plan(const uint8_t* data, uint64_t n, int kmer_bits, bool alt) {
     if (kmer_bits != 64 && kmer_bits != 128) throw FormatError("kmer_bits must be 64 or 128");
     ImagePlan P;
@@ -509,24 +568,7 @@ ImagePlan ImageBuilder::plan(const uint8_t* data, uint64_t n, int kmer_bits, boo
     if (img.m == 0 || img.m > 31 || img.k < img.m || img.k > uint32_t(kmer_bits / 2 - 1))
         throw FormatError("k/m out of range for this kmer_t");
     img.w = img.k - img.m + 1;
-    auto compact = [&](CompactRef& r) {
-        FileCompact f = c.compact();
-        r.size = f.size;
-        r.width = f.width;
-        r.words = VecRef{f.words, f.nwords};
-    };
-    auto ef = [&](EfRef& r) {
-        r.nbits = c.pod<uint64_t>();
-        r.high.p = c.vec<uint64_t>(r.high.n);
-        if ((r.nbits + 63) / 64 > r.high.n) throw FormatError("EF high bits shorter than declared");
-        r.positions = c.pod<uint64_t>();
-        uint64_t nb, ns, no;
-        c.vec<int64_t>(nb);
-        c.vec<uint16_t>(ns);
-        c.vec<uint64_t>(no);
-        compact(r.low);
-        if (r.low.size != r.positions) throw FormatError("EF: darray positions != number of values");
-    };
+    auto ef = [&](EfRef& r) { walk_ef(c, r); };
     auto bits = [&](BitsRef& r) {
         r.nbits = c.pod<uint64_t>();
         r.words.p = c.vec<uint64_t>(r.words.n);
@@ -535,32 +577,7 @@ ImagePlan ImageBuilder::plan(const uint8_t* data, uint64_t n, int kmer_bits, boo
         c.vec<uint64_t>(nh);
         if ((r.nbits + 63) / 64 > r.words.n) throw FormatError("bit vector shorter than declared");
     };
-    auto phf = [&](PhfRef& r, DevPhf& out) {
-        out.seed = c.pod<uint64_t>();
-        out.num_keys = c.pod<uint64_t>();
-        out.table_size = c.pod<uint64_t>();
-        c.pod<unsigned __int128>();
-        out.dense = c.pod<uint64_t>();
-        out.sparse = c.pod<uint64_t>();
-        c.pod<unsigned __int128>();
-        c.pod<unsigned __int128>();
-        compact(r.front_ranks);
-        compact(r.front_dict);
-        compact(r.back_ranks);
-        compact(r.back_dict);
-        r.n_buckets = r.front_ranks.size + r.back_ranks.size;
-        if (r.n_buckets != out.dense + out.sparse) throw FormatError("pilot count != bucket count");
-        if (out.table_size == 0 || out.table_size < out.num_keys) throw FormatError("single_phf: bad table size");
-        if (out.dense == 0 || out.sparse == 0) throw FormatError("single_phf: empty bucket class");
-        if (out.table_size >= (1ull << 31) || out.dense >= (1ull << 31) || out.sparse >= (1ull << 31))
-            throw FormatError("single_phf: table larger than 2^31 (impossible with 64-bit PTHash hashes)");
-        reciprocal64(out.table_size, out.m_table);
-        reciprocal64(out.dense, out.m_dense);
-        reciprocal64(out.sparse, out.m_sparse);
-        ef(r.free_slots);
-        r.n_free = out.table_size - out.num_keys;
-        if (r.free_slots.positions != r.n_free) throw FormatError("single_phf: free-slot count mismatch");
-    };
+    auto phf = [&](PhfRef& r, DevPhf& out) { walk_phf(c, r, out); };
     P.sections[0] = uint64_t(c.p - data);
     phf(P.minimizer_order, img.minimizer_order);
     P.sections[1] = uint64_t(c.p - data);

@@ -77,6 +77,8 @@ public:
     // Structure walk only (see ImagePlan): the same checks on sizes and ranges as parse / parse_alt, the same arena
     // layout, no decoding.  The references point into `data`, which must outlive the plan.
     static ImagePlan plan(const uint8_t* data, uint64_t n, int kmer_bits, bool alt);
+    // the same for a serialized pthash::single_phf on its own (build-p Part 3): plan.minimizer_order only
+    static ImagePlan plan_phf(const uint8_t* data, uint64_t n);
     // A serialized pthash::single_phf on its own (what build-p Part 3 evaluates, ref src/partitioned_mphf.cpp:
     // 96-100): afterwards the image holds `minimizer_order` only, free slots included.
     void parse_phf(const uint8_t* data, uint64_t n);
@@ -103,6 +105,9 @@ private:
     };
     Bits read_bits(Cursor& c);
     void read_phf(Cursor& c, DevPhf& out);
+    static void walk_compact(Cursor& c, CompactRef& r);
+    static void walk_ef(Cursor& c, EfRef& r);
+    static void walk_phf(Cursor& c, PhfRef& r, DevPhf& out);
     // the bucket table under construction, inside the arena (flag bits on top of the base: device_image.h)
     struct BucketWriter {
         uint8_t* p = nullptr;
