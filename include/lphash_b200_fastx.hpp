@@ -15,8 +15,10 @@
 // kseq reads through gzread one byte-buffer at a time (~9 ns/base); this works on the whole text in
 // memory with memchr (a few GB/s), which is what keeps the GPU path from waiting on the parser.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -33,6 +35,95 @@ struct Batch {
     std::vector<char> bases;         // all records' sequences, concatenated
     std::vector<uint64_t> offsets;   // n_records + 1 (offsets[0] = 0)
     uint64_t n_records() const { return offsets.empty() ? 0 : offsets.size() - 1; }
+};
+
+// ---- where the text comes from ----------------------------------------------------------------------------------
+// Plain file, gzip (one zlib stream on the calling thread, ~0.3 GB/s of text), or BGZF - the blocked gzip `bgzip`
+// writes (htslib; every block is a gzip member of at most 64 KB carrying its own size in a "BC" extra field):
+// there the blocks of a group are inflated side by side on `threads` threads (LPHB_INGEST_THREADS, default 8),
+// which is what lifts compressed input to the parser's speed.  read() fills at most `want` bytes, 0 = end.
+class TextSource {
+public:
+    explicit TextSource(std::string const& path) : path_(path) {
+#ifdef LPHASH_B200_WITH_ZLIB
+        raw_ = std::fopen(path.c_str(), "rb");
+        if (!raw_) throw std::runtime_error("cannot open " + path);
+        unsigned char h[18];
+        const size_t got = std::fread(h, 1, sizeof h, raw_);
+        std::rewind(raw_);
+        bgzf_ = got == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C' &&
+                h[14] == 2 && h[15] == 0;
+        if (const char* e = std::getenv("LPHB_INGEST_THREADS")) {
+            long v = std::strtol(e, nullptr, 10);
+            if (v >= 1) threads_ = unsigned(v > 64 ? 64 : v);
+        }
+        if (!bgzf_) {
+            std::fclose(raw_);
+            raw_ = nullptr;
+            gz_ = gzopen(path.c_str(), "rb");  // transparently reads uncompressed files too
+            if (!gz_) throw std::runtime_error("cannot open " + path);
+            gzbuffer(gz_, 1u << 20);
+        }
+#else
+        raw_ = std::fopen(path.c_str(), "rb");
+        if (!raw_) throw std::runtime_error("cannot open " + path);
+#endif
+    }
+    TextSource(TextSource const&) = delete;
+    TextSource& operator=(TextSource const&) = delete;
+    ~TextSource() {
+#ifdef LPHASH_B200_WITH_ZLIB
+        if (gz_) gzclose(gz_);
+#endif
+        if (raw_) std::fclose(raw_);
+    }
+    bool is_bgzf() const { return bgzf_; }
+
+    size_t read(char* dst, size_t want) {
+#ifdef LPHASH_B200_WITH_ZLIB
+        if (bgzf_) {
+            size_t done = 0;
+            while (done < want) {
+                if (out_pos_ == out_.size() && !refill()) break;
+                const size_t n = std::min(want - done, out_.size() - out_pos_);
+                std::memcpy(dst + done, out_.data() + out_pos_, n);
+                out_pos_ += n;
+                done += n;
+            }
+            return done;
+        }
+        int got = gzread(gz_, dst, unsigned(want > (1u << 30) ? (1u << 30) : want));
+        if (got < 0) throw std::runtime_error("read error in " + path_);
+        return size_t(got);
+#else
+        const size_t got = std::fread(dst, 1, want, raw_);
+        if (first_) {
+            first_ = false;
+            if (got >= 2 && (unsigned char)dst[0] == 0x1f && (unsigned char)dst[1] == 0x8b)
+                throw std::runtime_error(path_ + " is gzip-compressed: build with -DLPHASH_B200_WITH_ZLIB -lz");
+        }
+        return got;
+#endif
+    }
+
+private:
+#ifdef LPHASH_B200_WITH_ZLIB
+    struct Block {
+        size_t at, clen, out_at;  // deflate data inside comp_, its length, where the text goes
+        uint32_t isize, crc;
+    };
+    // the next group of blocks (about 32 MB of text), inflated in parallel into out_
+    bool refill();
+    gzFile gz_ = nullptr;
+    std::vector<unsigned char> comp_;
+    std::vector<char> out_;
+    size_t out_pos_ = 0;
+    bool eof_ = false;
+#endif
+    std::string path_;
+    std::FILE* raw_ = nullptr;
+    bool bgzf_ = false, first_ = true;
+    unsigned threads_ = 8;
 };
 
 // Appends the records of `data[0..n)` to `out` and returns how many bytes were consumed.
@@ -138,38 +229,16 @@ inline uint64_t parse(const char* data, size_t n, Batch& out) {
 // to `out`.  Throws std::runtime_error if the file cannot be read.
 inline uint64_t read_file(std::string const& path, Batch& out) {
     std::vector<char> text;
-#ifdef LPHASH_B200_WITH_ZLIB
-    gzFile f = gzopen(path.c_str(), "rb");  // transparently reads uncompressed files too
-    if (!f) throw std::runtime_error("cannot open " + path);
-    gzbuffer(f, 1u << 20);
+    TextSource src(path);
     size_t used = 0;
     text.resize(size_t(1) << 24);
     for (;;) {
         if (used == text.size()) text.resize(text.size() * 2);
-        const size_t want = text.size() - used;
-        int got = gzread(f, text.data() + used, unsigned(want > (1u << 30) ? (1u << 30) : want));
-        if (got < 0) {
-            gzclose(f);
-            throw std::runtime_error("read error in " + path);
-        }
+        const size_t got = src.read(text.data() + used, text.size() - used);
         if (got == 0) break;
-        used += size_t(got);
+        used += got;
     }
-    gzclose(f);
     text.resize(used);
-#else
-    std::FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) throw std::runtime_error("cannot open " + path);
-    std::fseek(f, 0, SEEK_END);
-    long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    text.resize(sz > 0 ? size_t(sz) : 0);
-    size_t got = text.empty() ? 0 : std::fread(text.data(), 1, text.size(), f);
-    std::fclose(f);
-    if (got != text.size()) throw std::runtime_error("short read in " + path);
-    if (text.size() >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b)
-        throw std::runtime_error(path + " is gzip-compressed: build with -DLPHASH_B200_WITH_ZLIB -lz");
-#endif
     return parse(text.data(), text.size(), out);
 }
 
@@ -192,6 +261,85 @@ inline uint64_t read_file(std::string const& path, Batch& out) {
 namespace lphash_b200 {
 namespace fastx {
 
+#ifdef LPHASH_B200_WITH_ZLIB
+inline bool TextSource::refill() {
+    out_.clear();
+    out_pos_ = 0;
+    if (eof_) return false;
+    comp_.clear();
+    std::vector<Block> blocks;
+    size_t text_bytes = 0;
+    while (text_bytes < (size_t(32) << 20)) {
+        unsigned char h[12];
+        const size_t got = std::fread(h, 1, sizeof h, raw_);
+        if (got == 0) {
+            eof_ = true;
+            break;
+        }
+        if (got != sizeof h || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4))
+            throw std::runtime_error("bad BGZF block header in " + path_);
+        const size_t xlen = size_t(h[10]) | (size_t(h[11]) << 8);
+        std::vector<unsigned char> extra(xlen);
+        if (std::fread(extra.data(), 1, xlen, raw_) != xlen) throw std::runtime_error("truncated BGZF block in " + path_);
+        size_t bsize = 0;
+        for (size_t i = 0; i + 4 <= xlen;) {  // subfields: SI1 SI2 SLEN(2) data
+            const size_t slen = size_t(extra[i + 2]) | (size_t(extra[i + 3]) << 8);
+            if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen)
+                bsize = (size_t(extra[i + 4]) | (size_t(extra[i + 5]) << 8)) + 1;
+            i += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8) throw std::runtime_error("BGZF block without a valid BC field in " + path_);
+        const size_t rest = bsize - 12 - xlen;  // deflate data + CRC32 + ISIZE
+        const size_t at = comp_.size();
+        comp_.resize(at + rest);
+        if (std::fread(comp_.data() + at, 1, rest, raw_) != rest) throw std::runtime_error("truncated BGZF block in " + path_);
+        const unsigned char* t = comp_.data() + at + rest - 8;
+        Block b;
+        b.at = at;
+        b.clen = rest - 8;
+        b.crc = uint32_t(t[0]) | (uint32_t(t[1]) << 8) | (uint32_t(t[2]) << 16) | (uint32_t(t[3]) << 24);
+        b.isize = uint32_t(t[4]) | (uint32_t(t[5]) << 8) | (uint32_t(t[6]) << 16) | (uint32_t(t[7]) << 24);
+        b.out_at = text_bytes;
+        text_bytes += b.isize;
+        if (b.isize) blocks.push_back(b);  // (the empty end-of-file marker block carries nothing)
+    }
+    if (blocks.empty()) return !eof_ ? refill() : false;
+    out_.resize(text_bytes);
+    const unsigned nt = unsigned(std::min<size_t>(threads_, blocks.size()));
+    std::vector<std::string> errs(nt);
+    auto work = [&](unsigned t) {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            errs[t] = "inflateInit2 failed";
+            return;
+        }
+        for (size_t i = t; i < blocks.size(); i += nt) {
+            Block const& b = blocks[i];
+            inflateReset(&zs);
+            zs.next_in = comp_.data() + b.at;
+            zs.avail_in = uInt(b.clen);
+            zs.next_out = reinterpret_cast<Bytef*>(out_.data() + b.out_at);
+            zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                uint32_t(crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const Bytef*>(out_.data() + b.out_at), b.isize)) != b.crc) {
+                errs[t] = "corrupt BGZF block in " + path_;
+                break;
+            }
+        }
+        inflateEnd(&zs);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (auto const& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    return true;
+}
+#endif
+
 template <class OnBatch>
 uint64_t stream_file(std::string const& path, size_t chunk_bytes, OnBatch&& on_batch) {
     if (chunk_bytes < 16) chunk_bytes = 16;
@@ -205,20 +353,8 @@ uint64_t stream_file(std::string const& path, size_t chunk_bytes, OnBatch&& on_b
     std::string error;
     std::thread producer([&]() {
         try {
-#ifdef LPHASH_B200_WITH_ZLIB
-            gzFile f = gzopen(path.c_str(), "rb");  // transparently reads uncompressed files too
-            if (!f) throw std::runtime_error("cannot open " + path);
-            gzbuffer(f, 1u << 20);
-            auto read_some = [&](char* dst, size_t want) -> size_t {
-                int got = gzread(f, dst, unsigned(want > (1u << 30) ? (1u << 30) : want));
-                if (got < 0) throw std::runtime_error("read error in " + path);
-                return size_t(got);
-            };
-#else
-            std::FILE* f = std::fopen(path.c_str(), "rb");
-            if (!f) throw std::runtime_error("cannot open " + path);
-            auto read_some = [&](char* dst, size_t want) -> size_t { return std::fread(dst, 1, want, f); };
-#endif
+            TextSource src(path);
+            auto read_some = [&](char* dst, size_t want) -> size_t { return src.read(dst, want); };
             std::vector<char> text;  // carry (the record held back) + the next chunk
             size_t carry = 0;
             int which = 0;
@@ -234,10 +370,6 @@ uint64_t stream_file(std::string const& path, size_t chunk_bytes, OnBatch&& on_b
                     }
                     got += r;
                 }
-#ifndef LPHASH_B200_WITH_ZLIB
-                if (carry == 0 && got >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b)
-                    throw std::runtime_error(path + " is gzip-compressed: build with -DLPHASH_B200_WITH_ZLIB -lz");
-#endif
                 const size_t n = carry + got;
                 Slot& s = slots[which];
                 {
@@ -256,11 +388,6 @@ uint64_t stream_file(std::string const& path, size_t chunk_bytes, OnBatch&& on_b
                 cv.notify_all();
                 which ^= 1;
             }
-#ifdef LPHASH_B200_WITH_ZLIB
-            gzclose(f);
-#else
-            std::fclose(f);
-#endif
         } catch (std::exception const& e) {
             std::lock_guard<std::mutex> lk(mu);
             error = e.what();
