@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     }
     const int bits = std::atoi(argv[2]);
     const int device = argc > 4 ? std::atoi(argv[4]) : 0;
-    const size_t chunk = (argc > 5 ? size_t(std::atoll(argv[5])) : 64) << 20;
+    const size_t chunk = (argc > 5 ? size_t(std::atoll(argv[5])) : 4) << 20;  // a few MB: small enough to overlap, large enough to fill the GPU
     bool use_runs = false, fold = true;
     for (int i = 6; i < argc; ++i) {
         if (std::strcmp(argv[i], "runs") == 0) use_runs = true;

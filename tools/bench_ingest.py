@@ -55,9 +55,13 @@ def main():
                            os.path.join(ROOT, "examples", "lphb_query.cpp"), "-o", exe, "-L", libdir, "-llphash_b200",
                            f"-Wl,-rpath,{libdir}", "-lz", "-pthread"])
     folds = set()
-    runs_list = [(fa, []), (fa, ["0", "64", "runs"]), (fa + ".gz", []), (fa + ".gz", ["0", "64", "runs"]),
-                 (bgz, []), (bgz, ["0", "64", "runs", "nofold"]),
-                 (fa, ["0", "64", "nofold"]), (fa, ["0", "64", "runs", "nofold"]), (fa + ".gz", ["0", "64", "runs", "nofold"])]
+    mb = os.environ.get("INGEST_CHUNK_MB", "4")  # chunk of text per batch (tools: INGEST_CHUNK_SWEEP=1 sweeps it)
+    runs_list = [(fa, ["0", mb]), (fa, ["0", mb, "runs"]), (fa + ".gz", ["0", mb]), (fa + ".gz", ["0", mb, "runs"]),
+                 (bgz, ["0", mb]), (bgz, ["0", mb, "runs"]),
+                 (fa, ["0", mb, "nofold"]), (fa, ["0", mb, "runs", "nofold"]), (fa + ".gz", ["0", mb, "nofold"]),
+                 (bgz, ["0", mb, "nofold"]), (bgz, ["0", mb, "runs", "nofold"])]
+    if os.environ.get("INGEST_CHUNK_SWEEP"):  # chunk-size sweep: plain text, codes and runs untouched
+        runs_list = [(fa, ["0", str(mb)] + extra + ["nofold"]) for mb in (2, 4, 8, 16, 32, 64) for extra in ([], ["runs"])]
     for path, form in runs_list:
         subprocess.check_output([exe, lph, "64", path] + form)  # warm-up: page cache, CUDA context
         t0 = time.perf_counter()
@@ -67,6 +71,7 @@ def main():
             folds.add(out[5])
         print(json.dumps({"row": "ingest", "impl": "lphash_b200 (examples/lphb_query.cpp, streaming ingest)",
                           "file": os.path.basename(path), "output": "runs" if "runs" in form else "codes",
+                          "chunk_mb": int(form[1]) if len(form) > 1 else 64,
                           "host_fold_of_every_code": "nofold" not in form, "kmers": int(out[2]),
                           "ns_per_kmer_end_to_end": float(out[3]), "ns_per_kmer_gpu_calls": float(out[4]),
                           "bases_per_s_end_to_end": float(out[6]), "process_wall_s": wall, "fold": out[5]}), flush=True)
