@@ -53,8 +53,9 @@ typedef struct lphb_info {
     uint64_t fallback_keys; /* k-mers handled by fallback_kmer_order */
     uint64_t file_bytes;    /* size of the .lph image parsed                                    */
     uint64_t device_bytes;  /* bytes of HBM the device image occupies                           */
-    double load_host_ms;    /* load time: parsing the image and building the flat arrays (host)  */
-    double load_h2d_ms;     /* load time: device allocation + the one host-to-device copy        */
+    double load_host_ms;    /* load time on the host: structure walk of the image (+ CUDA start-up if this
+                               is the process's first CUDA call; + the decode with LPHB_HOST_DECODE=1) */
+    double load_h2d_ms;     /* load time on the device: allocation, upload, decode kernels          */
 } lphb_info;
 
 const char* lphb_last_error(void);
@@ -63,8 +64,12 @@ int lphb_device_count(int* count);
 
 /* ---- loading: replaces essentials::load(hf, file) (src/query.cpp:37) ----------------------
  * Parses the byte-exact essentials visitor image of lphash::mphf
- * (include/partitioned_mphf.hpp:204-219) and uploads a flat device image.  kmer_bits selects the
- * fallback hash flavour of include/constants.hpp:56-70 (the file does not record it).          */
+ * (include/partitioned_mphf.hpp:204-219) and builds a flat device image from it.  The host only walks the
+ * structure (sizes, ranges: LPHB_E_FORMAT before any CUDA call for a malformed file); the decoding -
+ * compact_vector::access, Elias-Fano access, rs_bit_vector::rank, quartet_wtree::rank_of, one word per bucket -
+ * runs on the GPU (lphash_b200/csrc/image_decode.cu) and reports what only decoding reveals as
+ * LPHB_E_FORMAT too.  kmer_bits selects the fallback hash flavour of include/constants.hpp:56-70 (the
+ * file does not record it).                                                                      */
 int lphb_mphf_load_file(const char* path, int kmer_bits, int device, lphb_mphf** out);
 int lphb_mphf_load_memory(const void* image, uint64_t nbytes, int kmer_bits, int device,
                           lphb_mphf** out);
