@@ -7,7 +7,9 @@
 // Included after the reference's headers (configuration, kmer_t, pthash_*_mphf_t come from there).
 #pragma once
 #include <cstdlib>
+#include <algorithm>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -33,8 +35,22 @@ struct Parts {
     pthash::build_configuration cfg;
     lphash_b200::fastx::Batch input;
     uint64_t n_records = 0, nkmers = 0;
-    std::vector<lphash_b200::mm_triplet_t> triplets;  // one per distinct minimizer, ascending
-    std::vector<uint64_t> coll_ids;                   // ids of every occurrence of a colliding minimizer, ascending
+    // one triplet per distinct minimizer, ascending; ids of every occurrence of a colliding minimizer, ascending
+    // (uninitialised storage: at 2.5e9 k-mers a zero-filled worst-case vector would be tens of GB)
+    struct Triplets {
+        std::unique_ptr<lphash_b200::mm_triplet_t[]> p;
+        uint64_t n = 0;
+        const lphash_b200::mm_triplet_t* data() const { return p.get(); }
+        uint64_t size() const { return n; }
+        const lphash_b200::mm_triplet_t* begin() const { return p.get(); }
+        const lphash_b200::mm_triplet_t* end() const { return p.get() + n; }
+    } triplets;
+    struct Ids {
+        std::unique_ptr<uint64_t[]> p;
+        uint64_t n = 0;
+        const uint64_t* data() const { return p.get(); }
+        uint64_t size() const { return n; }
+    } coll_ids;
     std::vector<unsigned char> minimizer_order, fallback;  // the two serialized single_phf objects
 
     // Parts 1 and 2
@@ -52,21 +68,33 @@ struct Parts {
         if (config.verbose) std::cerr << "Part 1: file reading and info gathering\n";
         lphash_b200::fastx::read_file(config.input_filename.c_str(), input);
         n_records = input.n_records();
-        uint64_t cap = 1;
+        uint64_t max_kmers = 0;
         for (uint64_t c = 0; c < n_records; ++c) {
             const uint64_t len = input.offsets[c + 1] - input.offsets[c];
-            if (len >= k) cap += len - k + 1;
+            if (len >= k) max_kmers += len - k + 1;
         }
-        triplets.resize(cap);
-        coll_ids.resize(cap);
-        uint64_t mm_count = 0, n_triplets = 0, n_ids = 0;
-        check(lphb_scan_classify(device, k, m, config.mm_seed, input.bases.data(), input.offsets.data(), n_records, &mm_count,
-                                 triplets.data(), cap, &n_triplets, coll_ids.data(), cap, &n_ids, &nkmers));
-        triplets.resize(n_triplets);
-        coll_ids.resize(n_ids);
+        // super-k-mers are about 2 / (k - m + 2) of the k-mers; a third is room enough for every window of 5 or
+        // more (an input that needs more - LPHB_E_CAPACITY reports the counts - is scanned again with exactly that)
+        uint64_t cap = max_kmers / 3 + 4096, n_triplets = 0, n_ids = 0, mm_count = 0;
+        if (const char* e = std::getenv("LPHASH_B200_FIRST_CAP")) cap = std::strtoull(e, nullptr, 10) + 1;  // test hook
+        for (int attempt = 0;; ++attempt) {
+            triplets.p.reset(new lphash_b200::mm_triplet_t[cap]);
+            coll_ids.p.reset(new uint64_t[cap]);
+            mm_count = 0;
+            const int rc = lphb_scan_classify(device, k, m, config.mm_seed, input.bases.data(), input.offsets.data(), n_records,
+                                              &mm_count, triplets.p.get(), cap, &n_triplets, coll_ids.p.get(), cap, &n_ids, &nkmers);
+            if (rc == LPHB_E_CAPACITY && attempt == 0) {
+                cap = std::max(n_triplets, n_ids) + 1;
+                continue;
+            }
+            check(rc);
+            break;
+        }
+        triplets.n = n_triplets;
+        coll_ids.n = n_ids;
         if (config.verbose) std::cerr << "Part 2: build MPHF\n";
         std::vector<uint64_t> keys(n_triplets);
-        for (uint64_t i = 0; i < n_triplets; ++i) keys[i] = triplets[i].itself;
+        for (uint64_t i = 0; i < n_triplets; ++i) keys[i] = triplets.p[i].itself;
         pthash_minimizers_mphf_t f;
         f.build_in_external_memory(keys.begin(), n_triplets, cfg);
         lphash_b200::memory_saver saver;
@@ -79,13 +107,12 @@ struct Parts {
         if (config.verbose) std::cerr << "Part 4: build fallback MPHF\n";
         uint64_t n_coll_kmers = 0, mm_again = 0;
         const uint64_t kcap = coll_ids.size() * (uint64_t(k) - m + 1) + 1;  // a super-k-mer holds at most k - m + 1 k-mers
-        std::vector<kmer_t> kmers(kcap);
+        std::unique_ptr<kmer_t[]> kmers(new kmer_t[kcap]);
         check(lphb_colliding_kmers(device, k, m, config.mm_seed, input.bases.data(), input.offsets.data(), n_records, &mm_again,
-                                   coll_ids.data(), coll_ids.size(), int(sizeof(kmer_t) * 8), kmers.data(), kcap,
+                                   coll_ids.data(), coll_ids.size(), int(sizeof(kmer_t) * 8), kmers.get(), kcap,
                                    &n_coll_kmers));
-        kmers.resize(n_coll_kmers);
         pthash_fallback_mphf_t f;
-        f.build_in_external_memory(kmers.begin(), n_coll_kmers, cfg);
+        f.build_in_external_memory(kmers.get(), n_coll_kmers, cfg);
         lphash_b200::memory_saver saver;
         saver.visit(f);
         fallback.swap(saver.bytes);

@@ -20,6 +20,7 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 #include <ostream>
 #include <string>
 #include <type_traits>
@@ -49,16 +50,17 @@ public:
         p.scan_and_order(config);  // Parts 1 + 2
         if (config.verbose) std::cerr << "Part 3: build inverted index\n";
         lphb_inverted_index index{};
-        std::vector<unsigned char> body(lphb_inverted_index_bound(p.triplets.size()));
+        const uint64_t body_cap = lphb_inverted_index_bound(p.triplets.size());  // worst case; untouched beyond body_bytes
+        std::unique_ptr<unsigned char[]> body(new unsigned char[body_cap]);
         uint64_t body_bytes = 0;
         gpu_build::check(lphb_build_inverted_index(p.device, p.k, p.m, p.minimizer_order.data(), p.minimizer_order.size(),
-                                                   p.triplets.data(), p.triplets.size(), body.data(), body.size(),
+                                                   p.triplets.data(), p.triplets.size(), body.get(), body_cap,
                                                    &body_bytes, &index));
         p.fallback_function(config);  // Part 4
         std::vector<unsigned char> image(58 + p.minimizer_order.size() + body_bytes + p.fallback.size());
         uint64_t image_bytes = 0;
         gpu_build::check(lphb_lph_assemble(p.k, p.m, config.mm_seed, p.nkmers, p.triplets.size(), &index,
-                                           p.minimizer_order.data(), p.minimizer_order.size(), body.data(), body_bytes,
+                                           p.minimizer_order.data(), p.minimizer_order.size(), body.get(), body_bytes,
                                            p.fallback.data(), p.fallback.size(), image.data(), image.size(), &image_bytes));
         lphash_b200::memory_loader loader(image.data(), image_bytes);
         loader.visit(ref_);

@@ -12,6 +12,7 @@
 #include "unpartitioned_mphf_reference.hpp"
 #undef mphf_alt
 
+#include <memory>
 #include <ostream>
 #include <string>
 #include <type_traits>
@@ -37,16 +38,17 @@ public:
         p.scan_and_order(config);
         if (config.verbose) std::cerr << "Part 3: build inverted index\n";
         lphb_inverted_index_alt index{};
-        std::vector<unsigned char> body(lphb_inverted_index_bound(p.triplets.size()));
+        const uint64_t body_cap = lphb_inverted_index_bound(p.triplets.size());  // worst case; untouched beyond body_bytes
+        std::unique_ptr<unsigned char[]> body(new unsigned char[body_cap]);
         uint64_t body_bytes = 0;
         gpu_build::check(lphb_build_inverted_index_alt(p.device, p.minimizer_order.data(), p.minimizer_order.size(),
-                                                       p.triplets.data(), p.triplets.size(), body.data(), body.size(),
+                                                       p.triplets.data(), p.triplets.size(), body.get(), body_cap,
                                                        &body_bytes, &index));
         p.fallback_function(config);
         std::vector<unsigned char> image(34 + p.minimizer_order.size() + body_bytes + p.fallback.size());
         uint64_t image_bytes = 0;
         gpu_build::check(lphb_lph_assemble_alt(p.k, p.m, config.mm_seed, p.nkmers, p.triplets.size(), &index,
-                                               p.minimizer_order.data(), p.minimizer_order.size(), body.data(), body_bytes,
+                                               p.minimizer_order.data(), p.minimizer_order.size(), body.get(), body_bytes,
                                                p.fallback.data(), p.fallback.size(), image.data(), image.size(),
                                                &image_bytes));
         lphash_b200::memory_loader loader(image.data(), image_bytes);

@@ -104,11 +104,12 @@ def test_build_p_64_bit_flavour_and_cpu_switch(tmp_path):
             f.write(b">%d\n" % i + raw[int(off[i]):int(off[i + 1])] + b"\n")
     outs = {}
     for tag, cli, env in [("gpu", gpu64, None), ("ref", ref64, None),
+                          ("gpu_second_attempt", gpu64, {"LPHASH_B200_FIRST_CAP": "10"}),  # triplet buffer too small at first
                           ("cpu_switch", gpu64, {"LPHASH_B200_CPU_BUILD": "1"})]:
         out = str(tmp_path / (tag + ".lph"))
         csv, _, _ = run_build(cli, str(fa), 31, 20, out, str(tmp_path), env=env)
         outs[tag] = (csv, open(out, "rb").read())
-    assert outs["gpu"] == outs["ref"] == outs["cpu_switch"]
+    assert outs["gpu"] == outs["ref"] == outs["cpu_switch"] == outs["gpu_second_attempt"]
     assert outs["gpu"][1] == open(os.path.join(GOLDEN_DIR, "k31_m20_u64.lph"), "rb").read()
 
 
