@@ -597,6 +597,28 @@ def bench_cfg2(args, torch, dist, api, L, f, dev, stream, rank, world, bases, of
     ms_total, kern_ms, codes_s, runs_s, cc_s, cr_s = (float(x) for x in t.cpu())
     if rank != 0:
         return None
+    # the build-side scan of the same resident bases (minimizer::from_string stream; one fused kernel), beside the query
+    build_scan = None
+    try:
+        ms_l, nrec = [], 0
+        for _ in range(4):
+            _, nrec, nk_s, _, ms = api.scan_superkmers_device(d_bases.data_ptr(), d_off.data_ptr(), offsets, K, M,
+                                                              device=dev.index, fetch=False)
+            ms_l.append(ms)
+        assert nk_s == n_kmers
+        api.lib().lphb_scan_release(dev.index)
+        s_ms = float(np.mean(ms_l[1:]))
+        s_algo = int(offsets[-1] - offsets[0]) + 18 * int(nrec)
+        peaks = load_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        build_scan = {"metric": "build-p scan k-mers/sec (minimizer::from_string stream, bases resident)",
+                      "value": n_kmers / (s_ms * 1e-3), "unit": "k-mers/s", "kernel_ms": s_ms, "records": int(nrec),
+                      "roofline": {"bound": "hbm", "achieved": s_algo / (s_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": s_algo / (s_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": s_algo,
+                                   "kernel": "k_query_tiled<31,20,scan> (CUDA events around the kernel, mean of 3 launches)"},
+                      "parity": "tools/bench_rows.py scan: all records equal the reference's from_string stream"}
+    except Exception as e:  # the headline line stands without it
+        build_scan = {"unavailable": str(e)}
     value = world * n_kmers * args.steps / (ms_total * 1e-3)
     algo_bytes = int(offsets[-1] - offsets[0]) + 8 * n_kmers
     parts = {"codes_kmers": world * e["codes"]["kmers"], "codes_secs": codes_s, "runs_kmers": world * e["runs"]["kmers"],
@@ -613,6 +635,7 @@ def bench_cfg2(args, torch, dist, api, L, f, dev, stream, rank, world, bases, of
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline(algo_bytes, kern_ms, n_kmers,
                                  "k_query_tiled<31,20> (mean per launch over the timed region, CUDA events on the launching stream)"),
+            "build_scan": build_scan,
             "cpu_baseline": None}
 
 
