@@ -1095,7 +1095,18 @@ int scan_pass(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char*
     b.dirty = S.dirty.as<uint8_t>();
     S.n_records = 0;
     *n_dirty = 0;
-    if (n_kmers == 0) return LPHB_OK;
+    // the generic kernels (and a batch without any k-mer) never see the bytes of contigs shorter than k: look at them here
+    if (!pieces && (!tiled || n_kmers == 0)) launch_flag_invalid_bytes(d_bases, first, span, d_offsets, n_contigs, b.dirty, s);
+    if (n_kmers == 0) {
+        if (!pieces) {
+            launch_count_dirty(b.dirty, n_contigs, st, s);
+            unsigned long long h_st[2] = {0, 0};
+            CK(cudaMemcpyAsync(h_st, st, sizeof(h_st), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            *n_dirty = h_st[1];
+        }
+        return LPHB_OK;
+    }
     CK(cudaEventRecord(S.ev0, s));
     unsigned long long h_nrec = 0;
     if (tiled) {
@@ -1212,8 +1223,8 @@ int run_scan(ScanSession& S, uint32_t k, uint32_t m, uint64_t seed, const char* 
     S.n_records = 0;
     if (n_kmers >= (1ull << 32)) return fail(LPHB_E_ARG, "batch holds >= 2^32 k-mers: split it");
     if (!S.s) CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
-    if (n_contigs == 0 || n_kmers == 0) return LPHB_OK;
-    if (!bases) return fail(LPHB_E_ARG, "bases is null");
+    if (n_contigs == 0 || n_mmers == 0) return LPHB_OK;  // (without a k-mer there is no record, but an invalid byte
+    if (!bases) return fail(LPHB_E_ARG, "bases is null");  //  still changes the m-mer ordinals: the device decides)
     cudaStream_t s = S.s;
     const uint64_t first = offsets[0], span = offsets[n_contigs] - first;
     if (span >= (1ull << 32)) return fail(LPHB_E_ARG, "batch spans >= 2^32 bases: split it");
@@ -1342,7 +1353,7 @@ int lphb_scan_superkmers_device(int device, uint32_t k, uint32_t m, uint64_t see
         if (kernel_ms) *kernel_ms = 0;
         if (!S.s) CK(cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking));
         uint64_t mm_out = *mm_count + nm;
-        if (n_contigs && nk) {
+        if (n_contigs && nm) {
             if (!d_bases) return fail(LPHB_E_ARG, "d_bases is null");
             CK(cudaDeviceSynchronize());  // the caller's buffers may still be written on other streams
             ScanTrace tr;
@@ -1350,6 +1361,7 @@ int lphb_scan_superkmers_device(int device, uint32_t k, uint32_t m, uint64_t see
             if (rc != LPHB_OK) return rc;
             *d_records = S.records.p;
             *n_records = S.n_records;
+            *n_kmers = S.n_kmers;  // (differs from the count above when contigs hold non-ACGT bytes)
             if (kernel_ms) *kernel_ms = S.kernel_ms;
         }
         *mm_count = mm_out;

@@ -342,6 +342,27 @@ void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* po
     k_scan_emit<<<grid_for((b.n_kmers + 3) / 4), 256, 0, stream>>>(b, head, pos, rank, records, start_pos);
 }
 
+// every byte of the batch looked at once: contigs too short for a k-mer never reach the scan kernels, but an invalid
+// byte in them still matters to the m-mer ordinals (include/minimizer.hpp:45-49 counts valid runs only)
+__global__ void k_flag_invalid_bytes(const char* bases, uint64_t first, uint64_t span, const uint64_t* offsets,
+                                     uint64_t n_contigs, uint8_t* dirty) {
+    for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < span; p += uint64_t(gridDim.x) * blockDim.x) {
+        if (nt4(uint8_t(bases[first + p])) < 4) continue;
+        const uint64_t at = first + p;
+        uint64_t lo = 0, hi = n_contigs;  // offsets[lo] <= at < offsets[hi]
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= at) lo = mid; else hi = mid;
+        }
+        dirty[lo] = 1;
+    }
+}
+void launch_flag_invalid_bytes(const char* bases, uint64_t first, uint64_t span, const uint64_t* offsets, uint64_t n_contigs,
+                               uint8_t* dirty, cudaStream_t stream) {
+    if (!span || !n_contigs) return;
+    k_flag_invalid_bytes<<<grid_for(span), 256, 0, stream>>>(bases, first, span, offsets, n_contigs, dirty);
+}
+
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
                            uint64_t n_ids, uint32_t* take, cudaStream_t stream) {
     if (!n_records) return;

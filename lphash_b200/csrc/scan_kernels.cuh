@@ -38,6 +38,11 @@ uint64_t head_ranks_tmp_bytes(uint64_t n_kmers);
 void launch_scan_emit(ScanBatch const& b, const uint8_t* head, const uint8_t* pos,
                       const uint32_t* rank, uint8_t* records, uint32_t* start_pos, cudaStream_t stream);
 
+// dirty[c] = 1 for every contig holding a byte outside ACGT/acgt/U/u, whatever its length (the scan kernels only
+// look at contigs that hold a k-mer)
+void launch_flag_invalid_bytes(const char* bases, uint64_t first, uint64_t span, const uint64_t* offsets, uint64_t n_contigs,
+                               uint8_t* dirty, cudaStream_t stream);
+
 // get_colliding_kmers: take[r] = (record r's id is in ids) ? size : 0 ...
 void launch_colliding_mark(const uint8_t* records, uint64_t n_records, const uint64_t* ids,
                            uint64_t n_ids, uint32_t* take, cudaStream_t stream);

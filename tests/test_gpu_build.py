@@ -195,3 +195,29 @@ def test_build_input_with_non_acgt_bytes_matches_the_reference_loop(k, m):
     want3, _, _ = oracle.scan(clean, coff, k, m, mode=0)
     got3, _, _ = api.scan_superkmers(clean, coff, k, m)
     assert np.array_equal(got3, want3)
+
+
+@pytest.mark.parametrize("k,m", [(31, 20), (25, 13), (63, 24)])
+def test_invalid_bytes_in_contigs_too_short_for_a_kmer_still_count(k, m):
+    """m-mer ordinals advance over valid runs only (include/minimizer.hpp:45-49), also in contigs that hold no k-mer
+    and therefore never reach the scan kernels: the ids of every later record depend on them.  (Found by
+    tools/stress_parity.py: the generic kernels missed an `R` in a 24-base contig.)"""
+    from oracle import oracle
+    rng = np.random.default_rng(k + m)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    short = rng.choice(acgt, k - 1)
+    short[2] = ord("R")                      # m <= length < k, one invalid byte: 5 fewer m-mers than its length says
+    short2 = rng.choice(acgt, m + 1)
+    short2[m // 2] = ord("*")                # two runs shorter than m: no m-mer at all
+    contigs = [short, rng.choice(acgt, 400), short2, rng.choice(acgt, k), short.copy()]
+    bases = np.concatenate(contigs).astype(np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    want, wk, wmm = oracle.scan(bases, offsets, k, m, mode=0, mm_count=3)
+    got, gk, gmm = api.scan_superkmers(bases, offsets, k, m, mm_count=3)
+    assert (gk, gmm) == (wk, wmm) and np.array_equal(got, want)
+    # a batch without a single k-mer: nothing to scan, the ordinals still move by the valid m-mers only
+    only_short = np.concatenate([short, short2, short]).astype(np.uint8)
+    off2 = np.array([0, len(short), len(short) + len(short2), len(only_short)], dtype=np.uint64)
+    want2, wk2, wmm2 = oracle.scan(only_short, off2, k, m, mode=0, mm_count=7)
+    got2, gk2, gmm2 = api.scan_superkmers(only_short, off2, k, m, mm_count=7)
+    assert (len(got2), gk2, gmm2) == (len(want2), wk2, wmm2) == (0, 0, wmm2)

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Randomised parity stress (one-off, not part of the test suite): for every golden index, many random batches -
+substrings of the index sequence with substitutions, random sequence, lower case, N and junk bytes, lengths from 0
+to a few tiles, random batch sizes and base offsets - through the CUDA path (streaming query, run-length form,
+build scan, classify, colliding k-mers) against the CPU oracle.  usage: stress_parity.py [seconds] [seed]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import GOLDEN_NAMES, load_golden  # noqa: E402
+from lphash_b200 import api  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def random_batch(rng, g):
+    idx = g.index_bases
+    n = int(rng.integers(1, 60))
+    pieces = []
+    for _ in range(n):
+        kind = rng.integers(0, 10)
+        L = int(rng.choice([0, 1, g.m - 1, g.m, g.k - 1, g.k, g.k + 1, int(rng.integers(0, 200)), int(rng.integers(200, 3000)),
+                            int(rng.integers(900, 1100))]))
+        if kind < 5 and L < len(idx):
+            s0 = int(rng.integers(0, len(idx) - L))
+            p = idx[s0:s0 + L].copy()
+            if kind < 2 and L:
+                where = rng.integers(0, L, size=max(1, L // 80))
+                p[where] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(where))
+        else:
+            p = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L)
+        if kind == 7 and L:
+            p[rng.integers(0, L, size=int(rng.integers(1, 4)))] = rng.choice(np.frombuffer(b"N-nRY*", dtype=np.uint8))
+        if kind == 8 and L > 40:
+            a = int(rng.integers(0, L - 30))
+            p[a:a + int(rng.integers(1, 30))] = ord("N")
+        if kind == 9:
+            p = np.frombuffer(p.tobytes().lower(), dtype=np.uint8)
+        pieces.append(p.astype(np.uint8))
+    bases = np.concatenate(pieces) if pieces else np.zeros(0, np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(p) for p in pieces])]).astype(np.uint64)
+    return bases, offsets
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    handles = {n: api.Mphf.load(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
+    oracles = {n: oracle.OracleMphf(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
+    t_end = time.time() + seconds
+    rounds = 0
+    while time.time() < t_end:
+        for name in GOLDEN_NAMES:
+            g = load_golden(name)
+            bases, offsets = random_batch(rng, g)
+            os.environ["LPHB_GENERIC_BELOW"] = str(int(rng.choice([0, 1 << 18])))
+            if rng.random() < 0.3:
+                os.environ["LPHB_NO_SMALL_PATH"] = "1"
+            else:
+                os.environ.pop("LPHB_NO_SMALL_PATH", None)
+            f, o = handles[name], oracles[name]
+            want, want_off = o.query_batch(bases, offsets)
+            got, got_off = f.query_batch(bases, offsets)
+            fails = []
+            if not (np.array_equal(got_off, want_off) and np.array_equal(got, want)):
+                fails.append("query")
+            runs, _, n = f.query_batch_runs(bases, offsets)
+            if not np.array_equal(api.expand_runs(runs), want):
+                fails.append("runs")
+            rec_w, nk_w, mm_w = oracle.scan(bases, offsets, g.k, g.m, mode=0)
+            rec, nk, mm = api.scan_superkmers(bases, offsets, g.k, g.m)
+            if not ((nk, mm) == (nk_w, mm_w) and np.array_equal(rec, rec_w)):
+                fails.append(f"scan nk {nk}/{nk_w} mm {mm}/{mm_w} records {len(rec)}/{len(rec_w)}")
+            trip_w, ids_w = oracle.classify(rec_w)
+            trip, ids, _, _ = api.scan_classify(bases, offsets, g.k, g.m)
+            if not (np.array_equal(trip, trip_w) and np.array_equal(ids, ids_w)):
+                fails.append("classify")
+            km_w = oracle.colliding_kmers(bases, offsets, g.k, g.m, ids_w, kmer_bits=g.bits)
+            km = api.colliding_kmers(bases, offsets, g.k, g.m, ids_w, kmer_bits=g.bits)
+            if not np.array_equal(km, km_w):
+                fails.append(f"colliding k-mers {len(km)}/{len(km_w)}")
+            ok = not fails
+            if not ok:
+                print("failed:", fails, "env", os.environ.get("LPHB_GENERIC_BELOW"), os.environ.get("LPHB_NO_SMALL_PATH"), flush=True)
+                path = os.path.join(ROOT, "gpurun_out", f"stress_fail_{name}_{rounds}.npz")
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                np.savez_compressed(path, bases=bases, offsets=offsets)
+                print(f"MISMATCH {name} round {rounds}: batch saved to {path}", flush=True)
+                return 1
+        rounds += 1
+    print(f"stress ok: {rounds} rounds x {len(GOLDEN_NAMES)} indexes, seed {seed}", flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
