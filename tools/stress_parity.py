@@ -31,6 +31,13 @@ def random_batch(rng, g):
             if kind < 2 and L:
                 where = rng.integers(0, L, size=max(1, L // 80))
                 p[where] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(where))
+        elif kind == 5 and L:
+            # low complexity: homopolymers and short-period repeats (every window full of equal m-mers: the leftmost
+            # one wins, partitioned_mphf.hpp:124,152,159; hash-prefix ties everywhere)
+            unit = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), int(rng.integers(1, 7)))
+            p = np.tile(unit, L // len(unit) + 1)[:L].copy()
+            if L > 50 and rng.random() < 0.5:  # a few point changes inside the repeat
+                p[rng.integers(0, L, size=3)] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 3)
         else:
             p = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L)
         if kind == 7 and L:
@@ -51,7 +58,13 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
     handles = {n: api.Mphf.load(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
+    os.environ["LPHB_FORCE_WIDE_BUCKETS"] = "1"  # second set of handles: 64-bit bucket words
+    wide = {n: api.Mphf.load(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
+    del os.environ["LPHB_FORCE_WIDE_BUCKETS"]
     oracles = {n: oracle.OracleMphf(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
+    valid = np.zeros(256, dtype=bool)
+    for ch in b"ACGTUacgtu":
+        valid[ch] = True
     t_end = time.time() + seconds
     rounds = 0
     while time.time() < t_end:
@@ -63,12 +76,31 @@ def main():
                 os.environ["LPHB_NO_SMALL_PATH"] = "1"
             else:
                 os.environ.pop("LPHB_NO_SMALL_PATH", None)
-            f, o = handles[name], oracles[name]
+            f, o = (wide if rng.random() < 0.3 else handles)[name], oracles[name]
+            os.environ["LPHB_CHUNK_BASES"] = str(int(rng.choice([1, 300, 2000, 1 << 23])))  # chunk pipeline on / off
             want, want_off = o.query_batch(bases, offsets)
             got, got_off = f.query_batch(bases, offsets)
             fails = []
             if not (np.array_equal(got_off, want_off) and np.array_equal(got, want)):
                 fails.append("query")
+            # a sub-batch whose offsets do not start at zero
+            if len(offsets) > 4:
+                a, b2 = sorted(int(x) for x in rng.choice(len(offsets), size=2, replace=False))
+                if b2 > a:
+                    sub = offsets[a:b2 + 1]
+                    got_s, off_s = f.query_batch(bases, sub)
+                    if not (np.array_equal(got_s, want[int(want_off[a]):int(want_off[b2])]) and
+                            np.array_equal(off_s, want_off[a:b2 + 1] - want_off[a])):
+                        fails.append("sub-batch")
+            # non-streaming branch: invalid bytes count as 'A', every window of k bytes answered statelessly
+            clean = bases.copy()
+            clean[~valid[clean]] = ord("A")
+            ns_want = [o.query_stateless(clean[int(offsets[i]):int(offsets[i + 1])].tobytes())
+                       for i in range(len(offsets) - 1) if int(offsets[i + 1] - offsets[i]) >= g.k]
+            ns_want = np.concatenate(ns_want) if ns_want else np.zeros(0, np.uint64)
+            ns_got, _ = f.query_batch(bases, offsets, streaming=False)
+            if not np.array_equal(ns_got, ns_want):
+                fails.append("non-streaming")
             runs, _, n = f.query_batch_runs(bases, offsets)
             if not np.array_equal(api.expand_runs(runs), want):
                 fails.append("runs")
