@@ -206,6 +206,15 @@ class Mphf:
         _check(lib().lphb_copy_to_host(self.info.device, out.ctypes.data, ptr, n.value))
         return out.tobytes()
 
+    def dirty_flags(self) -> np.ndarray:
+        """per contig of the last query call: nonzero where the contig holds a byte outside ACGT/acgt/U/u"""
+        ptr, n = C.c_void_p(), C.c_uint64(0)
+        _check(lib().lphb_mphf_dirty_flags(self._h, C.byref(ptr), C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            _check(lib().lphb_copy_to_host(self.info.device, out.ctypes.data, ptr, n.value))
+        return out
+
     def stats(self) -> Stats:
         s = Stats()
         _check(lib().lphb_mphf_stats(self._h, C.byref(s)))

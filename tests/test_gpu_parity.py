@@ -529,3 +529,25 @@ def test_contig_seams_at_every_tile_alignment(name, handles):
     rec_w, nk_w, mm_w = oracle.scan(bases, offsets, g.k, g.m, mode=0)
     rec, nk, mm = api.scan_superkmers(bases, offsets, g.k, g.m)
     assert (nk, mm) == (nk_w, mm_w) and np.array_equal(rec, rec_w)
+
+
+@pytest.mark.parametrize("small_path", [True, False])
+def test_dirty_flags_of_the_last_call(golden, handles, small_path, monkeypatch):
+    """lphb_mphf_dirty_flags: one byte per contig of the last query call, nonzero where the contig holds a byte outside
+    ACGT/acgt/U/u - after a batch, and after single-record calls on the small-batch path"""
+    if not small_path:
+        monkeypatch.setenv("LPHB_NO_SMALL_PATH", "1")
+    f = handles(golden.name)
+    clean = np.array(golden.is_clean())
+    lens = np.diff(golden.q_offsets).astype(np.int64)
+    f.query_batch(golden.q_bases, golden.q_offsets)
+    flags = f.dirty_flags()
+    assert len(flags) == len(clean)
+    # a contig too short for a k-mer is never looked at by the query kernels: its flag is unspecified
+    look = lens >= golden.k
+    assert np.array_equal(flags[look] != 0, ~clean[look])
+    contigs = golden.contigs()
+    for i in [j for j in range(len(contigs)) if look[j]][:6] + [j for j in range(len(contigs)) if look[j] and not clean[j]][:3]:
+        f(contigs[i])
+        fl = f.dirty_flags()
+        assert len(fl) == 1 and bool(fl[0]) == (not clean[i]), i
