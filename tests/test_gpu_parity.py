@@ -551,3 +551,40 @@ def test_dirty_flags_of_the_last_call(golden, handles, small_path, monkeypatch):
         f(contigs[i])
         fl = f.dirty_flags()
         assert len(fl) == 1 and bool(fl[0]) == (not clean[i]), i
+
+
+def test_device_resident_calls_on_several_streams_share_one_handle():
+    """lphb_query_stream_device takes the caller's stream, the handle has one device workspace: back-to-back calls on
+    DIFFERENT streams (no host synchronisation in between) must not overlap in it - the library orders every call
+    behind the previous call's kernels - and each must deliver its own batch's codes."""
+    torch = pytest.importorskip("torch")
+    g = load_golden("k31_m20_u64")
+    f = api.Mphf.load(g.lph, g.bits)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    batches = []
+    genome = g.index_bases[: int(g.index_offsets[12])]
+    for i in range(12):  # batches of different sizes: different tile counts, different workspace footprints
+        bases, offsets = synth.reads(int(rng.integers(200, 6000)), genome, read_len=int(rng.integers(g.k, 400)), seed=100 + i)
+        want, want_off = f.query_batch(bases, offsets)
+        n = len(offsets) - 1
+        batches.append(dict(offsets=offsets, want=want,
+                            d_bases=torch.from_numpy(bases.copy()).to(dev),
+                            d_off=torch.from_numpy(offsets.astype(np.int64)).to(dev),
+                            d_codes=torch.zeros(len(want) + 1, dtype=torch.int64, device=dev),
+                            d_code_off=torch.empty(n + 1, dtype=torch.int64, device=dev),
+                            d_status=torch.zeros(4, dtype=torch.int64, device=dev)))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, b in enumerate(batches):
+            s = streams[(i + rep) % len(streams)]
+            f.query_device(b["d_bases"].data_ptr(), b["d_off"].data_ptr(), b["offsets"], b["d_codes"].data_ptr(), len(b["want"]),
+                           b["d_code_off"].data_ptr(), b["d_status"].data_ptr(), s.cuda_stream)
+        torch.cuda.synchronize()
+        for i, b in enumerate(batches):
+            st = b["d_status"].cpu().numpy()
+            assert st[0] == len(b["want"]) and st[1] == 0, (rep, i, st)
+            assert np.array_equal(b["d_codes"].cpu().numpy()[: len(b["want"])].view(np.uint64), b["want"]), (rep, i)
+            b["d_codes"].zero_()
+    f.close()
