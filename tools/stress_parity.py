@@ -19,12 +19,15 @@ from oracle import oracle  # noqa: E402
 
 def random_batch(rng, g):
     idx = g.index_bases
-    n = int(rng.integers(1, 60))
+    big = rng.random() < 0.08  # now and then a batch of a few hundred tiles (several CTAs per SM, many chunks)
+    n = int(rng.integers(200, 1500)) if big else int(rng.integers(1, 60))
     pieces = []
     for _ in range(n):
         kind = rng.integers(0, 10)
         L = int(rng.choice([0, 1, g.m - 1, g.m, g.k - 1, g.k, g.k + 1, int(rng.integers(0, 200)), int(rng.integers(200, 3000)),
                             int(rng.integers(900, 1100))]))
+        if big and rng.random() < 0.02:
+            L = int(rng.integers(5000, 40000))
         if kind < 5 and L < len(idx):
             s0 = int(rng.integers(0, len(idx) - L))
             p = idx[s0:s0 + L].copy()
