@@ -56,9 +56,43 @@ def random_batch(rng, g):
     return bases, offsets
 
 
+def main_alt(seconds, seed):
+    """the unpartitioned variant (mphf_alt, query-u) and, beside it, the partitioned one, against the UNMODIFIED
+    REFERENCE itself (oracle/_ref travels to the GPU box): streaming and non-streaming branch, record by record"""
+    from oracle import ref
+    rng = np.random.default_rng(seed)
+    cases = []
+    for name in ("k31_m20_u64", "k63_m24_u128", "k25_m13_u64"):
+        g = load_golden(name)
+        alt = os.path.join(os.path.dirname(g.lph), "alt_" + name + ".lph")
+        cases.append((g, api.Mphf.load_alt(alt, g.bits), ref.RefMphfAlt(alt, g.bits)))
+        cases.append((g, api.Mphf.load(g.lph, g.bits), ref.RefMphf(g.lph, g.bits)))
+    t_end = time.time() + seconds
+    rounds = 0
+    while time.time() < t_end:
+        for g, f, r in cases:
+            bases, offsets = random_batch(rng, g)
+            raw = bases.tobytes()
+            recs = [raw[int(offsets[i]):int(offsets[i + 1])] for i in range(len(offsets) - 1)]
+            for streaming in (True, False):
+                want = [r.query(c, streaming) for c in recs if streaming or len(c) >= g.k]
+                want = np.concatenate(want) if want else np.zeros(0, np.uint64)
+                got, _ = f.query_batch(bases, offsets, streaming=streaming)
+                if not np.array_equal(got, want):
+                    path = os.path.join(ROOT, "gpurun_out", f"stress_fail_alt_{g.name}_{rounds}.npz")
+                    np.savez_compressed(path, bases=bases, offsets=offsets)
+                    print(f"MISMATCH vs the reference ({type(r).__name__}, streaming={streaming}) {g.name}: saved to {path}", flush=True)
+                    return 1
+        rounds += 1
+    print(f"stress vs the reference ok: {rounds} rounds x {len(cases)} functions (3 mphf_alt, 3 mphf), seed {seed}", flush=True)
+    return 0
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    if len(sys.argv) > 3 and sys.argv[3] == "alt":
+        return main_alt(seconds, seed)
     rng = np.random.default_rng(seed)
     handles = {n: api.Mphf.load(load_golden(n).lph, load_golden(n).bits) for n in GOLDEN_NAMES}
     os.environ["LPHB_FORCE_WIDE_BUCKETS"] = "1"  # second set of handles: 64-bit bucket words
