@@ -294,7 +294,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def workload_config(n_kmers_requested, n_kmers):
@@ -455,9 +455,6 @@ def run_ours(args):
     bases, offsets, lph = make_workload(args.kmers)
     if world > 1:
         import datetime
-        # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...", printed to stdout
-        # when the environment sets NCCL_DEBUG) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"),
                                 timeout=datetime.timedelta(minutes=30))
     torch.cuda.set_device(local)
@@ -511,7 +508,7 @@ def run_ours(args):
                                         "cores": threads, "kind": "reference", "sample": sample}
             except Exception as e:  # the GPU result stands even if the reference .so is absent
                 line["cpu_baseline"] = {"unavailable": str(e)}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     f.close()
     if world > 1:
         dist.destroy_process_group()
@@ -739,7 +736,30 @@ def bench_cfg5(args, torch, dist, api, L, f, dev, stream, rank, world, index_bas
     return line
 
 
+# stdout carries the one JSON line and nothing else: libraries that print there (NCCL's version banner when the
+# environment sets NCCL_DEBUG) are sent to stderr for the whole run, the line goes to the original descriptor
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
