@@ -135,3 +135,30 @@ def test_unpartitioned_images_parse_and_cross_loading_is_rejected():
     for cut in (10, 58, len(img) // 2, len(img) - 1):
         buf = (C.c_char * cut).from_buffer_copy(img[:cut])
         assert L.lphb_mphf_alt_load_memory(C.addressof(buf), cut, 64, 0, C.byref(h)) == api.E_FORMAT
+
+
+def test_lph_sections_and_assemble_round_trip_on_the_host():
+    """host-only entry points: cutting a reference-written file into its parts (lphb_lph_sections) and putting it
+    together again (lphb_lph_assemble / _alt) gives the same bytes; sizes that do not add up are refused"""
+    import struct
+    for name, bits, alt in [("k31_m20_u64", 64, False), ("k63_m24_u128", 128, False), ("alt_k31_m20_u64", 64, True)]:
+        image = open(os.path.join(GOLDEN_DIR, name + ".lph"), "rb").read()
+        sec = api.lph_sections(image, bits, alt)
+        assert sec[0] == (34 if alt else 58) and sec[4] == len(image) and sec == sorted(sec)
+        mo, body, fb = image[sec[0]:sec[1]], image[sec[1]:sec[3]], image[sec[3]:sec[4]]
+        if alt:
+            k, m, seed, nkmers, distinct, main = struct.unpack_from("<BBQQQQ", image, 0)
+            idx = api.InvertedIndexAlt(num_kmers_in_main_index=main, positions_bytes=sec[2] - sec[1], sizes_bytes=sec[3] - sec[2])
+            out = api.lph_assemble_alt(k, m, seed, nkmers, distinct, idx, mo, body, fb)
+        else:
+            k, m, seed, nkmers, distinct, n_max, rs, ns, npos = struct.unpack_from("<BBQQQQQQQ", image, 0)
+            idx = api.InvertedIndex(n_maximal=n_max, right_coll_sizes_start=rs, none_sizes_start=ns, none_pos_start=npos,
+                                    wtree_bytes=sec[2] - sec[1], ef_bytes=sec[3] - sec[2])
+            out = api.lph_assemble(k, m, seed, nkmers, distinct, idx, mo, body, fb)
+            with pytest.raises(api.LphashError) as e:
+                api.lph_assemble(k, m, seed, nkmers, distinct, idx, mo, body[:-8], fb)
+            assert e.value.code == api.E_ARG
+        assert out == image
+    with pytest.raises(api.LphashError) as e:
+        api.lph_sections(image[:100], 64, True)
+    assert e.value.code == api.E_FORMAT
